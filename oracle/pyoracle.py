@@ -1,0 +1,224 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  PARITY UNPINNED: see oracle/catgen_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcatgen_oracle.so")
+
+G32UP, G32UPC, D32_ST3 = 0, 1, 2
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("catgen_oracle.c", "catgen_oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+class StepCfg(C.Structure):
+    _fields_ = [("B", C.c_int), ("d_iters", C.c_int), ("g_iters", C.c_int),
+                ("D_L1", C.c_float), ("D_L2", C.c_float), ("G_L1", C.c_float), ("G_L2", C.c_float),
+                ("D_clamp", C.c_float), ("G_clamp", C.c_float),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+def default_cfg(B, d_iters=1, g_iters=1):
+    """train.lua:20-48 defaults: D_L1=0 D_L2=1e-4 G_L1=G_L2=0 D_clamp=1 G_clamp=5; optim.adam defaults."""
+    return StepCfg(B, d_iters, g_iters, 0.0, 1e-4, 0.0, 0.0, 1.0, 5.0, 1e-3, 0.9, 0.999, 1e-8)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        build()
+    L = C.CDLL(_SO)
+    i, l, f, vp = C.c_int, C.c_long, C.c_float, C.c_void_p
+
+    def sig(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig("og_set_threads", None, i)
+    sig("og_get_threads", i)
+    sig("og_conv2d_fwd", None, _fp, _fp, _fp, _fp, i, i, i, i, i, i)
+    sig("og_conv2d_bwd_data", None, _fp, _fp, _fp, i, i, i, i, i, i)
+    sig("og_conv2d_bwd_filter", None, _fp, _fp, _fp, _fp, i, i, i, i, i, i)
+    sig("og_linear_fwd", None, _fp, _fp, _fp, _fp, i, i, i)
+    sig("og_linear_bwd", None, _fp, _fp, _fp, _fp, _fp, _fp, i, i, i)
+    sig("og_bn_fwd_train", None, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, i, i, i, f, f)
+    sig("og_bn_fwd_eval", None, _fp, _fp, _fp, _fp, _fp, _fp, i, i, i, f)
+    sig("og_bn_bwd_train", None, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, i, i, i)
+    sig("og_prelu_fwd", None, _fp, f, _fp, l)
+    sig("og_prelu_bwd", None, _fp, _fp, f, _fp, _fp, l)
+    sig("og_leakyrelu_fwd", None, _fp, f, _fp, l)
+    sig("og_leakyrelu_bwd", None, _fp, _fp, f, _fp, l)
+    sig("og_upsample2x_fwd", None, _fp, _fp, i, i, i)
+    sig("og_upsample2x_bwd", None, _fp, _fp, i, i, i)
+    sig("og_sigmoid_fwd", None, _fp, _fp, l)
+    sig("og_sigmoid_bwd", None, _fp, _fp, _fp, l)
+    sig("og_avgpool2_fwd", None, _fp, _fp, i, i, i)
+    sig("og_avgpool2_bwd", None, _fp, _fp, i, i, i)
+    sig("og_maxpool2_fwd", None, _fp, _fp, _ip, i, i, i)
+    sig("og_maxpool2_bwd", None, _fp, _ip, _fp, i, i, i)
+    sig("og_mask_channels", None, _fp, _fp, _fp, i, i)
+    sig("og_affine_matrix_fwd", None, _fp, _fp, i, i, i, i)
+    sig("og_affine_matrix_bwd", None, _fp, _fp, _fp, i, i, i, i)
+    sig("og_affine_grid_fwd", None, _fp, _fp, i, i, i)
+    sig("og_affine_grid_bwd", None, _fp, _fp, i, i, i)
+    sig("og_bilinear_fwd", None, _fp, _fp, _fp, i, i, i, i)
+    sig("og_bilinear_bwd", None, _fp, _fp, _fp, _fp, _fp, i, i, i, i)
+    sig("og_bce_fwd", f, _fp, _fp, i)
+    sig("og_bce_bwd", None, _fp, _fp, _fp, i)
+    sig("og_adam_step", None, _fp, _fp, _fp, _fp, l, i, f, f, f, f)
+    sig("og_conv_upsample_fwd", None, _fp, _fp, _fp, _fp, i, i, i, i, i, i, i)
+    sig("og_model_create", vp, i, i, i)
+    sig("og_model_free", None, vp)
+    sig("og_model_nparams", l, vp)
+    sig("og_model_params", _fp, vp)
+    sig("og_model_grads", _fp, vp)
+    sig("og_model_bn_running", _fp, vp, C.POINTER(l))
+    sig("og_model_init", None, vp, C.c_ulonglong)
+    sig("og_model_zero_grads", None, vp)
+    sig("og_D_mask_floats", l, i)
+    sig("og_G_forward", None, vp, _fp, i, _fp, i)
+    sig("og_G_backward", None, vp, _fp, _fp)
+    sig("og_D_forward", None, vp, _fp, i, _fp, _fp, _fp)
+    sig("og_D_backward", None, vp, _fp, _fp)
+    sig("og_trainer_create", vp, vp, vp)
+    sig("og_trainer_free", None, vp)
+    sig("og_train_step", None, vp, C.POINTER(StepCfg), _fp, _fp, _fp, _fp, _fp, _fp, _fp)
+    sig("og_fevalD", f, vp, C.POINTER(StepCfg), _fp, _fp, _fp, _fp)
+    sig("og_fevalG_on_D", f, vp, C.POINTER(StepCfg), _fp, _fp)
+    _lib = L
+    return L
+
+
+def P(a):
+    """float32 C-contiguous ndarray (or None) -> float*"""
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(_fp)
+
+
+def IP(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_ip)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Model:
+    """Oracle G or D with parameters as a flat vector in nn getParameters() order."""
+
+    def __init__(self, kind, C_img=3, nz=100, seed=None):
+        self.L = lib()
+        self.kind, self.C, self.nz = kind, C_img, nz
+        self.h = self.L.og_model_create(kind, C_img, nz)
+        self.n = self.L.og_model_nparams(self.h)
+        if seed is not None:
+            self.L.og_model_init(self.h, seed)
+
+    def __del__(self):
+        try:
+            self.L.og_model_free(self.h)
+        except Exception:
+            pass
+
+    @property
+    def params(self):
+        return np.ctypeslib.as_array(self.L.og_model_params(self.h), shape=(self.n,))
+
+    @property
+    def grads(self):
+        return np.ctypeslib.as_array(self.L.og_model_grads(self.h), shape=(self.n,))
+
+    @property
+    def bn_running(self):
+        n = C.c_long()
+        p = self.L.og_model_bn_running(self.h, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(n.value,)) if n.value else np.zeros(0, np.float32)
+
+    def zero_grads(self):
+        self.L.og_model_zero_grads(self.h)
+
+    def G_forward(self, z, train=True):
+        z = f32(z)
+        B = z.shape[0]
+        out = np.empty((B, self.C, 32, 32), np.float32)
+        self.L.og_G_forward(self.h, P(z), B, P(out), 1 if train else 0)
+        return out
+
+    def G_backward(self, gout):
+        gout = f32(gout)
+        gz = np.empty((gout.shape[0], self.nz), np.float32)
+        self.L.og_G_backward(self.h, P(gout), P(gz))
+        return gz
+
+    def D_forward(self, x, masks=None):
+        x = f32(x)
+        B = x.shape[0]
+        sig, pre = np.empty(B, np.float32), np.empty(B, np.float32)
+        if masks is not None:
+            masks = f32(masks)
+            assert masks.size == self.L.og_D_mask_floats(B)
+        self.L.og_D_forward(self.h, P(x), B, P(masks), P(sig), P(pre))
+        return sig, pre
+
+    def D_backward(self, gout):
+        gout = f32(gout)
+        gx = np.empty((gout.shape[0], self.C, 32, 32), np.float32)
+        self.L.og_D_backward(self.h, P(gout), P(gx))
+        return gx
+
+
+def D_mask_floats(B):
+    return lib().og_D_mask_floats(B)
+
+
+def make_D_masks(B, rng):
+    """Train-mode dropout multipliers in the layout og_D_forward expects."""
+    sp = (rng.random(B * (64 * 4 + 128)) >= 0.2).astype(np.float32)          # 5x SpatialDropout(0.2), no rescale
+    head = (rng.random(B * 320) >= 0.5).astype(np.float32)                   # SpatialDropout(0.5)
+    fc = (rng.random(B * 256) >= 0.5).astype(np.float32) * 2.0               # Dropout(0.5), rescaled by 1/(1-p)
+    return np.concatenate([sp, head, fc]).astype(np.float32)
+
+
+class Trainer:
+    def __init__(self, G, D):
+        self.L = lib()
+        self.G, self.D = G, D
+        self.h = self.L.og_trainer_create(G.h, D.h)
+
+    def __del__(self):
+        try:
+            self.L.og_trainer_free(self.h)
+        except Exception:
+            pass
+
+    def step(self, cfg, real, zD, zG, masks=None):
+        real, zD, zG = f32(real), f32(zD), f32(zG)
+        lossD = np.zeros(cfg.d_iters, np.float32)
+        lossG = np.zeros(cfg.g_iters, np.float32)
+        d_out = np.zeros(cfg.B, np.float32)
+        if masks is not None:
+            masks = f32(masks)
+        self.L.og_train_step(self.h, C.byref(cfg), P(real), P(zD), P(zG), P(masks), P(lossD), P(lossG), P(d_out))
+        return lossD, lossG, d_out

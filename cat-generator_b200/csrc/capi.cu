@@ -1,0 +1,558 @@
+// capi.cu -- extern "C" surface declared in include/catgen.h.  Host pointers in, host pointers out; all
+// compute happens in this library's CUDA kernels (no CPU fallback: cg_init fails without an sm_100 device).
+#include "model.cuh"
+#include <math.h>
+#include <new>
+#ifdef CG_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace cg {
+Ctx& ctx() { static Ctx c; return c; }
+int set_err(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(ctx().err, sizeof(ctx().err), fmt, ap); va_end(ap);
+  return code;
+}
+static void* grow(void** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes && *p) return *p;
+  cudaStreamSynchronize(ctx().stream);
+  if (*p) cudaFree(*p);
+  size_t want = bytes + bytes / 4 + 4096;
+  if (cudaMalloc(p, want) != cudaSuccess) { *p = nullptr; *cap = 0; set_err(CG_ERR_CUDA, "cudaMalloc(%zu) failed", want); return nullptr; }
+  *cap = want;
+  return *p;
+}
+void* workspace(size_t bytes) { return grow(&ctx().ws, &ctx().ws_bytes, bytes); }
+void* workspace2(size_t bytes) { return grow(&ctx().ws2, &ctx().ws2_bytes, bytes); }
+void* pinned(size_t bytes) {
+  Ctx& c = ctx();
+  if (c.pinned_bytes >= bytes && c.pinned) return c.pinned;
+  cudaStreamSynchronize(c.stream);
+  if (c.pinned) cudaFreeHost(c.pinned);
+  if (cudaMallocHost(&c.pinned, bytes + 4096) != cudaSuccess) { c.pinned = nullptr; c.pinned_bytes = 0; return nullptr; }
+  c.pinned_bytes = bytes + 4096;
+  return c.pinned;
+}
+int DBuf::ensure(size_t nfloats) {
+  if (n >= nfloats && p) return CG_OK;
+  if (p) { cudaStreamSynchronize(ctx().stream); cudaFree(p); p = nullptr; n = 0; }
+  if (nfloats == 0) nfloats = 1;
+  if (cudaMalloc(&p, sizeof(float) * nfloats) != cudaSuccess) { p = nullptr; return set_err(CG_ERR_CUDA, "cudaMalloc(%zu floats) failed", nfloats); }
+  n = nfloats;
+  return CG_OK;
+}
+void DBuf::release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+
+// per-call temporary device buffers for the op-level entry points (unit-parity surface; not the hot path)
+struct Tmp {
+  std::vector<void*> v; bool ok = true;
+  float* dev(size_t n) { void* p = nullptr; if (cudaMalloc(&p, sizeof(float) * (n ? n : 1)) != cudaSuccess) { ok = false; return nullptr; } v.push_back(p); return (float*)p; }
+  float* up(const float* h, size_t n) {
+    float* d = dev(n); if (!d) return nullptr;
+    if (cudaMemcpyAsync(d, h, sizeof(float) * n, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess) ok = false;
+    return d;
+  }
+  int down(float* h, const float* d, size_t n) {
+    if (cudaMemcpyAsync(h, d, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx().stream) != cudaSuccess) return set_err(CG_ERR_CUDA, "D2H failed");
+    return CG_OK;
+  }
+  int finish() {
+    cudaError_t e = cudaStreamSynchronize(ctx().stream);
+    if (e != cudaSuccess) return set_err(CG_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    return ok ? CG_OK : set_err(CG_ERR_CUDA, "temporary device allocation/copy failed");
+  }
+  ~Tmp() { cudaStreamSynchronize(ctx().stream); for (void* p : v) cudaFree(p); }
+};
+}  // namespace cg
+using namespace cg;
+
+extern "C" {
+
+int cg_init(int device) {
+  Ctx& c = ctx();
+  if (c.inited) { if (c.device == device) return CG_OK; return set_err(CG_ERR_STATE, "already initialised on device %d", c.device); }
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return set_err(CG_ERR_NODEVICE, "no CUDA device: libcatgen has no CPU fallback (B200 / sm_100a required)");
+  if (device < 0 || device >= n) return set_err(CG_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  CG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p; CG_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return set_err(CG_ERR_NODEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
+  c.sm_count = p.multiProcessorCount;
+  CG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.device = device; c.inited = true; c.launches = 0;
+  return CG_OK;
+}
+void cg_shutdown(void) {
+  Ctx& c = ctx();
+  if (!c.inited) return;
+  cudaStreamSynchronize(c.stream);
+#ifdef CG_WITH_NCCL
+  if (c.nccl) { ncclCommDestroy((ncclComm_t)c.nccl); c.nccl = nullptr; }
+#endif
+  if (c.ws) cudaFree(c.ws); if (c.ws2) cudaFree(c.ws2); if (c.pinned) cudaFreeHost(c.pinned);
+  c.ws = c.ws2 = c.pinned = nullptr; c.ws_bytes = c.ws2_bytes = c.pinned_bytes = 0;
+  cudaStreamDestroy(c.stream); c.stream = nullptr; c.inited = false; c.device = -1; c.world = 1; c.rank = 0;
+}
+const char* cg_last_error(void) { return ctx().err; }
+const char* cg_version(void) { return "catgen-b200 0.1 (sm_100a)"; }
+int cg_sync(void) { CG_REQUIRE_INIT(); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
+int64_t cg_launch_count(void) { return ctx().launches; }
+void cg_reset_launch_count(void) { ctx().launches = 0; }
+int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
+int cg_get_conv_engine(void) { return ctx().conv_engine; }
+
+// ------------------------------------------------------------------ models
+int cg_model_create(cg_model** out, int kind, int C, int nz, uint64_t seed) {
+  CG_REQUIRE_INIT(); CG_ARG(out); CG_ARG(C == 1 || C == 3); CG_ARG(nz > 0);
+  cg_model* m = new (std::nothrow) cg_model();
+  if (!m) return set_err(CG_ERR_STATE, "out of host memory");
+  m->kind = kind; m->C = C; m->nz = nz; m->seed = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  int s = model_build(m);
+  if (s != CG_OK) { delete m; return s; }
+  CG_CUDA(cudaStreamSynchronize(ctx().stream));
+  *out = m; return CG_OK;
+}
+int cg_model_free(cg_model* m) {
+  if (!m) return CG_OK;
+  cudaStreamSynchronize(ctx().stream);
+  if (m->P) cudaFree(m->P); if (m->G) cudaFree(m->G); if (m->packed) cudaFree(m->packed); if (m->run) cudaFree(m->run);
+  if (m->masks) cudaFree(m->masks); if (m->mq) cudaFree(m->mq);
+  for (auto& b : m->fw) b.release(); for (auto& b : m->bw) b.release(); m->gwp.release();
+  delete m; return CG_OK;
+}
+int cg_model_nparams(const cg_model* m, int64_t* n) { CG_ARG(m && n); *n = m->np; return CG_OK; }
+int cg_model_get_params(cg_model* m, float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(m && host);
+  CG_CUDA(cudaMemcpyAsync(host, m->P, sizeof(float) * m->np, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_model_set_params(cg_model* m, const float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(m && host);
+  CG_CUDA(cudaMemcpyAsync(m->P, host, sizeof(float) * m->np, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream));
+  m->dirty = true; return CG_OK;
+}
+int cg_model_get_grads(cg_model* m, float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(m && host);
+  CG_CUDA(cudaMemcpyAsync(host, m->G, sizeof(float) * m->np, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_model_zero_grads(cg_model* m) { CG_REQUIRE_INIT(); CG_ARG(m); CG_CUDA(cudaMemsetAsync(m->G, 0, sizeof(float) * m->np, ctx().stream)); return CG_OK; }
+int cg_model_bn_running_len(const cg_model* m, int64_t* n) { CG_ARG(m && n); *n = m->nrun; return CG_OK; }
+int cg_model_get_bn_running(cg_model* m, float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(m && host); if (!m->nrun) return CG_OK;
+  CG_CUDA(cudaMemcpyAsync(host, m->run, sizeof(float) * m->nrun, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_model_set_bn_running(cg_model* m, const float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(m && host); if (!m->nrun) return CG_OK;
+  CG_CUDA(cudaMemcpyAsync(m->run, host, sizeof(float) * m->nrun, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_model_set_mode(cg_model* m, int training) { CG_ARG(m); m->training = training ? 1 : 0; return CG_OK; }
+
+int cg_G_forward(cg_model* g, const float* z, int B, float* out) {
+  CG_REQUIRE_INIT(); CG_ARG(g && z && out && B > 0); CG_ARG(g->kind != CG_D32_ST3);
+  size_t nz = (size_t)B * g->nz, no = (size_t)B * g->C * 1024;
+  float* st = (float*)workspace2(sizeof(float) * (nz + no)); if (!st) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemcpyAsync(st, z, sizeof(float) * nz, cudaMemcpyHostToDevice, ctx().stream));
+  CG_TRY(G_forward_dev(g, st, B, st + nz));
+  CG_CUDA(cudaMemcpyAsync(out, st + nz, sizeof(float) * no, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_G_backward(cg_model* g, const float* gout, float* gz) {
+  CG_REQUIRE_INIT(); CG_ARG(g && gout); CG_ARG(g->kind != CG_D32_ST3);
+  int B = g->B; size_t no = (size_t)B * g->C * 1024, nz = (size_t)B * g->nz;
+  float* st = (float*)workspace2(sizeof(float) * (no + nz)); if (!st) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemcpyAsync(st, gout, sizeof(float) * no, cudaMemcpyHostToDevice, ctx().stream));
+  CG_TRY(G_backward_dev(g, st, st + no));
+  if (gz) CG_CUDA(cudaMemcpyAsync(gz, st + no, sizeof(float) * nz, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_D_forward(cg_model* d, const float* x, int B, float* out_sig, float* out_pre) {
+  CG_REQUIRE_INIT(); CG_ARG(d && x && B > 0); CG_ARG(d->kind == CG_D32_ST3);
+  size_t nx = (size_t)B * d->C * 1024;
+  float* st = (float*)workspace2(sizeof(float) * (nx + 2 * (size_t)B)); if (!st) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemcpyAsync(st, x, sizeof(float) * nx, cudaMemcpyHostToDevice, ctx().stream));
+  CG_TRY(D_forward_dev(d, st, B, st + nx, st + nx + B));
+  if (out_sig) CG_CUDA(cudaMemcpyAsync(out_sig, st + nx, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx().stream));
+  if (out_pre) CG_CUDA(cudaMemcpyAsync(out_pre, st + nx + B, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_D_backward(cg_model* d, const float* gout, float* gx) {
+  CG_REQUIRE_INIT(); CG_ARG(d && gout); CG_ARG(d->kind == CG_D32_ST3);
+  int B = d->B; size_t nx = (size_t)B * d->C * 1024;
+  float* st = (float*)workspace2(sizeof(float) * (nx + (size_t)B)); if (!st) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemcpyAsync(st, gout, sizeof(float) * B, cudaMemcpyHostToDevice, ctx().stream));
+  CG_TRY(D_backward_dev(d, st, st + B));
+  if (gx) CG_CUDA(cudaMemcpyAsync(gx, st + B, sizeof(float) * nx, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_D_mask_floats(int B, int64_t* n) { CG_ARG(n && B > 0); *n = D_mask_floats(B); return CG_OK; }
+int cg_D_get_masks(cg_model* d, float* host) {
+  CG_REQUIRE_INIT(); CG_ARG(d && host); if (!d->masks || !d->masks_B) return set_err(CG_ERR_STATE, "no forward has run yet");
+  CG_CUDA(cudaMemcpyAsync(host, d->masks, sizeof(float) * D_mask_floats(d->masks_B), cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_D_set_masks(cg_model* d, const float* host, int B, int count) {
+  CG_REQUIRE_INIT(); CG_ARG(d && host && B > 0 && count > 0);
+  size_t n = (size_t)D_mask_floats(B) * count;
+  if (d->mq) { cudaStreamSynchronize(ctx().stream); cudaFree(d->mq); d->mq = nullptr; }
+  CG_CUDA(cudaMalloc(&d->mq, sizeof(float) * n));
+  CG_CUDA(cudaMemcpyAsync(d->mq, host, sizeof(float) * n, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream));
+  d->mq_count = count; d->mq_next = 0; d->mq_B = B; return CG_OK;
+}
+
+// ------------------------------------------------------------------ criterion / optimiser
+int cg_bce(const float* p, const float* t, int n, float* loss, float* g) {
+  CG_REQUIRE_INIT(); CG_ARG(p && t && n > 0);
+  Tmp T; float* dp = T.up(p, n); float* dt = T.up(t, n); float* dg = T.dev(n); float* dl = T.dev(1);
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(bce(dp, dt, n, dl, dg));
+  if (loss) CG_TRY(T.down(loss, dl, 1)); if (g) CG_TRY(T.down(g, dg, n));
+  return T.finish();
+}
+int cg_penalty_clamp(cg_model* m, float l1, float l2sign, float l2, float clampv, float* loss_add) {
+  CG_REQUIRE_INIT(); CG_ARG(m);
+  Tmp T; float* dl = T.dev(1); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(penalty_clamp(m->G, m->P, m->np, l1, l2sign, l2, clampv, dl));
+  if (loss_add) CG_TRY(T.down(loss_add, dl, 1));
+  return T.finish();
+}
+int cg_trainer_create(cg_trainer** out, cg_model* G, cg_model* D) {
+  CG_REQUIRE_INIT(); CG_ARG(out && G && D); CG_ARG(G->kind != CG_D32_ST3 && D->kind == CG_D32_ST3 && G->C == D->C);
+  cg_trainer* t = new (std::nothrow) cg_trainer(); if (!t) return set_err(CG_ERR_STATE, "out of host memory");
+  t->G = G; t->D = D;
+  CG_CUDA(cudaMalloc(&t->mD, sizeof(float) * D->np)); CG_CUDA(cudaMalloc(&t->vD, sizeof(float) * D->np));
+  CG_CUDA(cudaMalloc(&t->mG, sizeof(float) * G->np)); CG_CUDA(cudaMalloc(&t->vG, sizeof(float) * G->np));
+  CG_CUDA(cudaMemsetAsync(t->mD, 0, sizeof(float) * D->np, ctx().stream)); CG_CUDA(cudaMemsetAsync(t->vD, 0, sizeof(float) * D->np, ctx().stream));
+  CG_CUDA(cudaMemsetAsync(t->mG, 0, sizeof(float) * G->np, ctx().stream)); CG_CUDA(cudaMemsetAsync(t->vG, 0, sizeof(float) * G->np, ctx().stream));
+  *out = t; return CG_OK;
+}
+int cg_trainer_free(cg_trainer* t) {
+  if (!t) return CG_OK;
+  cudaStreamSynchronize(ctx().stream);
+  cudaFree(t->mD); cudaFree(t->vD); cudaFree(t->mG); cudaFree(t->vG);
+  t->inputs.release(); t->targets.release(); t->samples.release(); t->dout.release(); t->df.release(); t->gimg.release(); t->scal.release();
+  t->stage.release();
+  delete t; return CG_OK;
+}
+int cg_adam_step(cg_trainer* t, int which, const cg_step_cfg* cfg) {
+  CG_REQUIRE_INIT(); CG_ARG(t && cfg && (which == 0 || which == 1));
+  if (which == 0) { t->tD += 1; CG_TRY(adam(t->D->P, t->D->G, t->mD, t->vD, t->D->np, t->tD, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->D->dirty = true; }
+  else { t->tG += 1; CG_TRY(adam(t->G->P, t->G->G, t->mG, t->vG, t->G->np, t->tG, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->G->dirty = true; }
+  return CG_OK;
+}
+
+int cg_dist_allreduce_grads(cg_model* m) {
+  CG_REQUIRE_INIT(); CG_ARG(m);
+  if (ctx().world <= 1) return CG_OK;
+#ifdef CG_WITH_NCCL
+  // sum over ranks then scale by 1/world: BCE is a mean over the LOCAL batch
+  ncclResult_t r = ncclAllReduce(m->G, m->G, (size_t)m->np, ncclFloat, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
+  return scale_inplace(m->G, 1.f / ctx().world, m->np);
+#else
+  return set_err(CG_ERR_NCCL, "library built without NCCL");
+#endif
+}
+
+// one adversarial.train loop body on device-resident inputs.  scal: [lossD(d_iters), pen(d_iters), lossG(g_iters), pen(g_iters)]
+static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* real, const float* zD, const float* zG, float* lossD, float* lossG) {
+  cg_model *G = t->G, *D = t->D;
+  int B = c->B, hB = B / 2, C = G->C, nz = G->nz; size_t img = (size_t)C * 1024;
+  CG_ARG(B >= 4 && B % 2 == 0);   // adversarial.lua:65-68 skips batches smaller than 4
+  CG_TRY(t->inputs.ensure(B * img)); CG_TRY(t->targets.ensure(2 * (size_t)B)); CG_TRY(t->samples.ensure(B * img));
+  CG_TRY(t->dout.ensure(B)); CG_TRY(t->df.ensure(B)); CG_TRY(t->gimg.ensure(B * img));
+  int ns = 2 * (c->d_iters + c->g_iters); CG_TRY(t->scal.ensure(ns));
+  float* tgtD = t->targets.p; float* tgtG = t->targets.p + B;
+  CG_TRY(fill(tgtD, 1.f, hB)); CG_TRY(fill(tgtD + hB, 0.f, B - hB)); CG_TRY(fill(tgtG, 1.f, B));   // Y_NOT_GENERATOR=1, Y_GENERATOR=0 (train.lua:70-71)
+  int si = 0;
+  for (int k = 0; k < c->d_iters; ++k) {
+    // (1.1) real half, (1.2) fake half from a separate G forward on B/2 noise vectors (adversarial.lua:223-238)
+    CG_CUDA(cudaMemcpyAsync(t->inputs.p, real + (size_t)k * hB * img, sizeof(float) * hB * img, cudaMemcpyDeviceToDevice, ctx().stream));
+    CG_TRY(G_forward_dev(G, zD + (size_t)k * hB * nz, hB, t->inputs.p + hB * img));
+    // fevalD (adversarial.lua:72-167)
+    CG_CUDA(cudaMemsetAsync(D->G, 0, sizeof(float) * D->np, ctx().stream));
+    CG_TRY(D_forward_dev(D, t->inputs.p, B, t->dout.p, nullptr));
+    CG_TRY(bce(t->dout.p, tgtD, B, t->scal.p + si, t->df.p));
+    CG_TRY(D_backward_dev(D, t->df.p, nullptr));
+    CG_TRY(cg_dist_allreduce_grads(D));
+    CG_TRY(penalty_clamp(D->G, D->P, D->np, c->D_L1, c->D_L1, c->D_L2, c->D_clamp, t->scal.p + si + 1));
+    si += 2;
+    t->tD += 1; CG_TRY(adam(D->P, D->G, t->mD, t->vD, D->np, t->tD, c->lr, c->beta1, c->beta2, c->eps)); D->dirty = true;   // :245
+  }
+  for (int k = 0; k < c->g_iters; ++k) {
+    // fevalG_on_D (adversarial.lua:171-215)
+    CG_CUDA(cudaMemsetAsync(G->G, 0, sizeof(float) * G->np, ctx().stream));
+    CG_TRY(G_forward_dev(G, zG + (size_t)k * B * nz, B, t->samples.p));
+    CG_TRY(D_forward_dev(D, t->samples.p, B, nullptr, nullptr));   // t->dout keeps the last D-phase outputs for d_out
+    float* dsig = D->hsig;
+    CG_TRY(bce(dsig, tgtG, B, t->scal.p + si, t->df.p));
+    CG_TRY(D_backward_dev(D, t->df.p, t->gimg.p));   // also accumulates into D's grads, like the reference (zeroed by the next fevalD)
+    CG_TRY(G_backward_dev(G, t->gimg.p, nullptr));
+    CG_TRY(cg_dist_allreduce_grads(G));
+    CG_TRY(penalty_clamp(G->G, G->P, G->np, c->G_L1, c->G_L2, c->G_L2, c->G_clamp, t->scal.p + si + 1));   // sign term uses G_L2 (adversarial.lua:206)
+    si += 2;
+    t->tG += 1; CG_TRY(adam(G->P, G->G, t->mG, t->vG, G->np, t->tG, c->lr, c->beta1, c->beta2, c->eps)); G->dirty = true;   // :262
+  }
+  if (lossD || lossG) {
+    float* h = (float*)pinned(sizeof(float) * ns); if (!h) return set_err(CG_ERR_CUDA, "pinned alloc failed");
+    CG_CUDA(cudaMemcpyAsync(h, t->scal.p, sizeof(float) * ns, cudaMemcpyDeviceToHost, ctx().stream));
+    CG_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (int k = 0; k < c->d_iters; ++k) if (lossD) lossD[k] = h[2 * k] + h[2 * k + 1];
+    for (int k = 0; k < c->g_iters; ++k) if (lossG) lossG[k] = h[2 * (c->d_iters + k)] + h[2 * (c->d_iters + k) + 1];
+  }
+  return CG_OK;
+}
+int cg_train_step_dev(cg_trainer* t, const cg_step_cfg* cfg, const float* real_dev, const float* zD_dev, const float* zG_dev, float* lossD, float* lossG) {
+  CG_REQUIRE_INIT(); CG_ARG(t && cfg && real_dev && zD_dev && zG_dev);
+  return train_step_core(t, cfg, real_dev, zD_dev, zG_dev, lossD, lossG);
+}
+int cg_train_step(cg_trainer* t, const cg_step_cfg* cfg, const float* real, const float* zD, const float* zG, float* lossD, float* lossG, float* d_out) {
+  CG_REQUIRE_INIT(); CG_ARG(t && cfg && real && zD && zG);
+  int B = cfg->B, hB = B / 2; size_t img = (size_t)t->G->C * 1024, nz = t->G->nz;
+  size_t nr = (size_t)cfg->d_iters * hB * img, nzd = (size_t)cfg->d_iters * hB * nz, nzg = (size_t)cfg->g_iters * B * nz;
+  CG_TRY(t->stage.ensure(nr + nzd + nzg));
+  float* s = t->stage.p;
+  CG_CUDA(cudaMemcpyAsync(s, real, sizeof(float) * nr, cudaMemcpyHostToDevice, ctx().stream));
+  CG_CUDA(cudaMemcpyAsync(s + nr, zD, sizeof(float) * nzd, cudaMemcpyHostToDevice, ctx().stream));
+  CG_CUDA(cudaMemcpyAsync(s + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyHostToDevice, ctx().stream));
+  float ld[16], lg[16]; CG_ARG(cfg->d_iters <= 16 && cfg->g_iters <= 16);
+  // D's outputs of the last D update must be captured before the G phase overwrites dout
+  CG_TRY(train_step_core(t, cfg, s, s + nr, s + nr + nzd, ld, lg));
+  if (lossD) for (int k = 0; k < cfg->d_iters; ++k) lossD[k] = ld[k];
+  if (lossG) for (int k = 0; k < cfg->g_iters; ++k) lossG[k] = lg[k];
+  if (d_out) { CG_CUDA(cudaMemcpyAsync(d_out, t->dout.p, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); }
+  return CG_OK;
+}
+void* cg_dev_alloc(int64_t bytes) { if (!ctx().inited) return nullptr; void* p = nullptr; if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr; return p; }
+int cg_dev_free(void* p) { if (p) { cudaStreamSynchronize(ctx().stream); cudaFree(p); } return CG_OK; }
+int cg_dev_upload(void* dst, const void* src, int64_t bytes) { CG_REQUIRE_INIT(); CG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
+int cg_dev_download(void* dst, const void* src, int64_t bytes) { CG_REQUIRE_INIT(); CG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
+int cg_uniform_dev(float* dst, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset) { CG_REQUIRE_INIT(); return uniform(dst, n, lo, hi, seed, offset); }
+
+// ------------------------------------------------------------------ data parallel
+int cg_dist_unique_id(char id_out[128]) {
+#ifdef CG_WITH_NCCL
+  ncclUniqueId id; ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id_out, &id, 128); return CG_OK;
+#else
+  (void)id_out; return set_err(CG_ERR_NCCL, "library built without NCCL");
+#endif
+}
+int cg_dist_init(int rank, int world, const char id[128]) {
+  CG_REQUIRE_INIT(); CG_ARG(world >= 1 && rank >= 0 && rank < world);
+  if (world == 1) { ctx().rank = 0; ctx().world = 1; return CG_OK; }
+#ifdef CG_WITH_NCCL
+  ncclUniqueId uid; memcpy(&uid, id, 128);
+  ncclComm_t comm; ncclResult_t r = ncclCommInitRank(&comm, world, uid, rank);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  ctx().nccl = comm; ctx().rank = rank; ctx().world = world; return CG_OK;
+#else
+  (void)id; return set_err(CG_ERR_NCCL, "library built without NCCL");
+#endif
+}
+int cg_dist_world(void) { return ctx().world; }
+
+// ------------------------------------------------------------------ op level (Torch NCHW host tensors)
+static int conv_op_args(int N, int Ci, int H, int W, int Co, int k) {
+  if (N <= 0 || Ci <= 0 || H <= 0 || W <= 0 || Co <= 0) return set_err(CG_ERR_ARG, "non-positive conv dimension");
+  if (k <= 0 || k % 2 == 0) return set_err(CG_ERR_ARG, "kW/kH has to be odd");   // layers/SpatialConvolutionUpsample.lua:5-7
+  return CG_OK;
+}
+int cg_conv2d_fprop(const float* x, const float* W, const float* b, float* y, int N, int Ci, int H, int Wd, int Co, int k) {
+  CG_REQUIRE_INIT(); CG_ARG(x && W && y); CG_TRY(conv_op_args(N, Ci, H, Wd, Co, k));
+  Tmp T; size_t nx = (size_t)N * Ci * H * Wd, ny = (size_t)N * Co * H * Wd, nW = (size_t)Co * Ci * k * k;
+  float *dx = T.up(x, nx), *dW = T.up(W, nW), *db = b ? T.up(b, Co) : nullptr, *xh = T.dev(nx), *Wp = T.dev(nW), *yh = T.dev(ny), *dy = T.dev(ny);
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  ConvSpec s; s.Ci = Ci; s.Co = Co; s.k = k;
+  CG_TRY(nchw_to_nhwc(dx, xh, N, Ci, H * Wd)); CG_TRY(pack_fprop(dW, Wp, s));
+  CG_TRY(conv_fwd(xh, Wp, db, yh, N, H, Wd, Ci, Co, k));
+  CG_TRY(nhwc_to_nchw(yh, dy, N, Co, H * Wd)); CG_TRY(T.down(y, dy, ny));
+  return T.finish();
+}
+int cg_conv2d_dgrad(const float* gy, const float* W, float* gx, int N, int Ci, int H, int Wd, int Co, int k) {
+  CG_REQUIRE_INIT(); CG_ARG(gy && W && gx); CG_TRY(conv_op_args(N, Ci, H, Wd, Co, k));
+  Tmp T; size_t nx = (size_t)N * Ci * H * Wd, ny = (size_t)N * Co * H * Wd, nW = (size_t)Co * Ci * k * k;
+  float *dg = T.up(gy, ny), *dW = T.up(W, nW), *gh = T.dev(ny), *Wdp = T.dev(nW), *xh = T.dev(nx), *dx = T.dev(nx);
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  ConvSpec s; s.Ci = Ci; s.Co = Co; s.k = k;
+  CG_TRY(nchw_to_nhwc(dg, gh, N, Co, H * Wd)); CG_TRY(pack_dgrad(dW, Wdp, s));
+  CG_TRY(conv_dgrad(gh, Wdp, xh, N, H, Wd, Ci, Co, k));
+  CG_TRY(nhwc_to_nchw(xh, dx, N, Ci, H * Wd)); CG_TRY(T.down(gx, dx, nx));
+  return T.finish();
+}
+int cg_conv2d_wgrad(const float* x, const float* gy, float* gW, float* gb, int N, int Ci, int H, int Wd, int Co, int k) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gy && gW); CG_TRY(conv_op_args(N, Ci, H, Wd, Co, k));
+  Tmp T; size_t nx = (size_t)N * Ci * H * Wd, ny = (size_t)N * Co * H * Wd, nW = (size_t)Co * Ci * k * k;
+  float *dx = T.up(x, nx), *dg = T.up(gy, ny), *xh = T.dev(nx), *gh = T.dev(ny), *gwp = T.dev(nW), *dgW = T.up(gW, nW), *dgb = gb ? T.up(gb, Co) : nullptr;
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  ConvSpec s; s.Ci = Ci; s.Co = Co; s.k = k;
+  CG_TRY(nchw_to_nhwc(dx, xh, N, Ci, H * Wd)); CG_TRY(nchw_to_nhwc(dg, gh, N, Co, H * Wd));
+  CG_TRY(conv_wgrad(xh, gh, gwp, N, H, Wd, Ci, Co, k)); CG_TRY(unpack_wgrad_acc(gwp, dgW, s));   // accumulates, like accGradParameters
+  if (dgb) CG_TRY(colsum_acc(gh, dgb, (long)N * H * Wd, Co));
+  CG_TRY(T.down(gW, dgW, nW)); if (gb) CG_TRY(T.down(gb, dgb, Co));
+  return T.finish();
+}
+int cg_conv_upsample_fwd(const float* x, const float* W, const float* b, float* y, int N, int Ci, int H, int Wd, int nOut, int k, int f) {
+  CG_ARG(f >= 1 && nOut > 0);
+  // parent conv to nOut*f*f planes; the :view to [N,nOut,H*f,W*f] does not move memory (SpatialConvolutionUpsample.lua:21)
+  return cg_conv2d_fprop(x, W, b, y, N, Ci, H, Wd, nOut * f * f, k);
+}
+int cg_conv_upsample_bwd(const float* x, const float* gy, const float* W, float* gx, float* gW, float* gb, int N, int Ci, int H, int Wd, int nOut, int k, int f) {
+  CG_ARG(f >= 1 && nOut > 0);
+  // gradOutput is viewed back to [N,nOut*f*f,H,W] (SpatialConvolutionUpsample.lua:30-47): same memory
+  if (gx) CG_TRY(cg_conv2d_dgrad(gy, W, gx, N, Ci, H, Wd, nOut * f * f, k));
+  if (gW) CG_TRY(cg_conv2d_wgrad(x, gy, gW, gb, N, Ci, H, Wd, nOut * f * f, k));
+  return CG_OK;
+}
+int cg_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int in, int out) {
+  CG_REQUIRE_INIT(); CG_ARG(x && W && y && N > 0 && in > 0 && out > 0);
+  Tmp T; float *dx = T.up(x, (size_t)N * in), *dW = T.up(W, (size_t)in * out), *db = b ? T.up(b, out) : nullptr, *Wp = T.dev((size_t)in * out), *dy = T.dev((size_t)N * out);
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  ConvSpec s; s.Ci = in; s.Co = out; s.k = 1;
+  CG_TRY(pack_fprop(dW, Wp, s)); CG_TRY(conv_fwd(dx, Wp, db, dy, N, 1, 1, in, out, 1)); CG_TRY(T.down(y, dy, (size_t)N * out));
+  return T.finish();
+}
+int cg_linear_bwd(const float* x, const float* gy, const float* W, float* gx, float* gW, float* gb, int N, int in, int out) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gy && W && N > 0 && in > 0 && out > 0);
+  Tmp T; size_t nW = (size_t)in * out;
+  float *dx = T.up(x, (size_t)N * in), *dg = T.up(gy, (size_t)N * out), *dW = T.up(W, nW), *Wdp = T.dev(nW), *dgx = T.dev((size_t)N * in), *gwp = T.dev(nW);
+  float *dgW = gW ? T.up(gW, nW) : nullptr, *dgb = gb ? T.up(gb, out) : nullptr;
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  ConvSpec s; s.Ci = in; s.Co = out; s.k = 1;
+  if (gx) { CG_TRY(pack_dgrad(dW, Wdp, s)); CG_TRY(conv_dgrad(dg, Wdp, dgx, N, 1, 1, in, out, 1)); CG_TRY(T.down(gx, dgx, (size_t)N * in)); }
+  if (gW) { CG_TRY(conv_wgrad(dx, dg, gwp, N, 1, 1, in, out, 1)); CG_TRY(unpack_wgrad_acc(gwp, dgW, s)); CG_TRY(T.down(gW, dgW, nW)); }
+  if (gb) { CG_TRY(colsum_acc(dg, dgb, N, out)); CG_TRY(T.down(gb, dgb, out)); }
+  return T.finish();
+}
+int cg_bn2d_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_invstd, float* run_mean, float* run_var, int N, int C, int HW) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gamma && beta && y && N > 0 && C > 0 && HW > 0);
+  Tmp T; size_t n = (size_t)N * C * HW;
+  float *dx = T.up(x, n), *xh = T.dev(n), *yh = T.dev(n), *dy = T.dev(n), *dg = T.up(gamma, C), *db = T.up(beta, C), *dm = T.dev(C), *di = T.dev(C);
+  float *drm = run_mean ? T.up(run_mean, C) : nullptr, *drv = run_var ? T.up(run_var, C) : nullptr;
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(nchw_to_nhwc(dx, xh, N, C, HW));
+  CG_TRY(bn_fwd_train(xh, dg, db, yh, dm, di, drm, drv, (long)N * HW, C, 1e-5f, 0.1f));
+  CG_TRY(nhwc_to_nchw(yh, dy, N, C, HW)); CG_TRY(T.down(y, dy, n));
+  if (save_mean) CG_TRY(T.down(save_mean, dm, C)); if (save_invstd) CG_TRY(T.down(save_invstd, di, C));
+  if (run_mean) CG_TRY(T.down(run_mean, drm, C)); if (run_var) CG_TRY(T.down(run_var, drv, C));
+  return T.finish();
+}
+int cg_bn2d_bwd(const float* x, const float* gy, const float* gamma, const float* save_mean, const float* save_invstd, float* gx, float* ggamma, float* gbeta, int N, int C, int HW) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gy && gamma && save_mean && save_invstd && N > 0 && C > 0 && HW > 0);
+  Tmp T; size_t n = (size_t)N * C * HW;
+  float *dx = T.up(x, n), *dgy = T.up(gy, n), *xh = T.dev(n), *gh = T.dev(n), *gxh = T.dev(n), *dgx = T.dev(n);
+  float *dg = T.up(gamma, C), *dm = T.up(save_mean, C), *di = T.up(save_invstd, C);
+  float *dgg = ggamma ? T.up(ggamma, C) : nullptr, *dgb = gbeta ? T.up(gbeta, C) : nullptr;
+  if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(nchw_to_nhwc(dx, xh, N, C, HW)); CG_TRY(nchw_to_nhwc(dgy, gh, N, C, HW));
+  CG_TRY(bn_bwd(xh, gh, dg, dm, di, gx ? gxh : nullptr, dgg, dgb, (long)N * HW, C));
+  if (gx) { CG_TRY(nhwc_to_nchw(gxh, dgx, N, C, HW)); CG_TRY(T.down(gx, dgx, n)); }
+  if (ggamma) CG_TRY(T.down(ggamma, dgg, C)); if (gbeta) CG_TRY(T.down(gbeta, dgb, C));
+  return T.finish();
+}
+int cg_prelu_fwd(const float* x, float w, float* y, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && n > 0);
+  Tmp T; float *dx = T.up(x, n), *dw = T.up(&w, 1), *dy = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(prelu_fwd(dx, dw, dy, n)); CG_TRY(T.down(y, dy, n)); return T.finish();
+}
+int cg_prelu_bwd(const float* x, const float* gy, float w, float* gx, float* gw, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gy && n > 0);
+  Tmp T; float *dx = T.up(x, n), *dg = T.up(gy, n), *dw = T.up(&w, 1), *dgx = T.dev(n), *dgw = gw ? T.up(gw, 1) : nullptr; if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(prelu_bwd(dx, dg, dw, gx ? dgx : nullptr, dgw, n));
+  if (gx) CG_TRY(T.down(gx, dgx, n)); if (gw) CG_TRY(T.down(gw, dgw, 1)); return T.finish();
+}
+int cg_leakyrelu_fwd(const float* x, float s, float* y, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && n > 0);
+  Tmp T; float *dx = T.up(x, n), *dy = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(lrelu_fwd(dx, s, dy, n)); CG_TRY(T.down(y, dy, n)); return T.finish();
+}
+int cg_leakyrelu_bwd(const float* x, const float* gy, float s, float* gx, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(x && gy && gx && n > 0);
+  Tmp T; float *dx = T.up(x, n), *dg = T.up(gy, n), *dgx = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(lrelu_bwd(dx, dg, s, dgx, n)); CG_TRY(T.down(gx, dgx, n)); return T.finish();
+}
+int cg_sigmoid_fwd(const float* x, float* y, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && n > 0);
+  Tmp T; float *dx = T.up(x, n), *dy = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(sigmoid_fwd(dx, dy, n)); CG_TRY(T.down(y, dy, n)); return T.finish();
+}
+int cg_sigmoid_bwd(const float* y, const float* gy, float* gx, int64_t n) {
+  CG_REQUIRE_INIT(); CG_ARG(y && gy && gx && n > 0);
+  Tmp T; float *dy = T.up(y, n), *dg = T.up(gy, n), *dgx = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(sigmoid_bwd(dy, dg, dgx, n)); CG_TRY(T.down(gx, dgx, n)); return T.finish();
+}
+// NCHW planes are independent for these ops: run the NHWC kernels with C = 1 and N = NC
+int cg_upsample2x_fwd(const float* x, float* y, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && NC > 0 && H > 0 && Wd > 0);
+  Tmp T; size_t n = (size_t)NC * H * Wd; float *dx = T.up(x, n), *dy = T.dev(4 * n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(upsample2x_fwd(dx, dy, NC, H, Wd, 1)); CG_TRY(T.down(y, dy, 4 * n)); return T.finish();
+}
+int cg_upsample2x_bwd(const float* gy, float* gx, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(gy && gx && NC > 0 && H > 0 && Wd > 0);
+  Tmp T; size_t n = (size_t)NC * H * Wd; float *dg = T.up(gy, 4 * n), *dx = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(upsample2x_bwd(dg, dx, NC, H, Wd, 1)); CG_TRY(T.down(gx, dx, n)); return T.finish();
+}
+int cg_avgpool2_fwd(const float* x, float* y, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && NC > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)NC * H * Wd, no = (size_t)NC * (H / 2) * (Wd / 2); float *dx = T.up(x, n), *dy = T.dev(no); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(avgpool2_fwd(dx, dy, NC, H, Wd, 1)); CG_TRY(T.down(y, dy, no)); return T.finish();
+}
+int cg_avgpool2_bwd(const float* gy, float* gx, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(gy && gx && NC > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)NC * H * Wd, no = (size_t)NC * (H / 2) * (Wd / 2); float *dg = T.up(gy, no), *dx = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(avgpool2_bwd(dg, dx, NC, H, Wd, 1)); CG_TRY(T.down(gx, dx, n)); return T.finish();
+}
+__global__ void k_u8_to_i32(const uint8_t* a, int32_t* b, long n, int dir) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) { if (dir == 0) b[i] = a[i]; else ((uint8_t*)a)[i] = (uint8_t)b[i]; }
+}
+int cg_maxpool2_fwd(const float* x, float* y, int32_t* idx, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(x && y && NC > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)NC * H * Wd, no = (size_t)NC * (H / 2) * (Wd / 2);
+  float *dx = T.up(x, n), *dy = T.dev(no); uint8_t* di = (uint8_t*)T.dev(no / 4 + 4); int32_t* di32 = (int32_t*)T.dev(no); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(maxpool2_fwd(dx, dy, di, NC, H, Wd, 1)); CG_TRY(T.down(y, dy, no));
+  if (idx) { CG_LAUNCH(k_u8_to_i32, grid1d(no, 256), 256, 0, di, di32, (long)no, 0); CG_TRY(T.down((float*)idx, (float*)di32, no)); }
+  return T.finish();
+}
+int cg_maxpool2_bwd(const float* gy, const int32_t* idx, float* gx, int NC, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(gy && idx && gx && NC > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)NC * H * Wd, no = (size_t)NC * (H / 2) * (Wd / 2);
+  float *dg = T.up(gy, no), *dx = T.dev(n); int32_t* di32 = (int32_t*)T.up((const float*)idx, no); uint8_t* di = (uint8_t*)T.dev(no / 4 + 4); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_LAUNCH(k_u8_to_i32, grid1d(no, 256), 256, 0, di, di32, (long)no, 1);
+  CG_TRY(maxpool2_bwd(dg, di, dx, NC, H, Wd, 1)); CG_TRY(T.down(gx, dx, n)); return T.finish();
+}
+static int nth_of(int rot, int scl, int trn) { return (rot ? 1 : 0) + (scl ? 1 : 0) + (trn ? 2 : 0); }
+int cg_affine_matrix_fwd(const float* theta, float* A, int B, int rot, int scl, int trn) {
+  CG_REQUIRE_INIT(); CG_ARG(theta && A && B > 0 && nth_of(rot, scl, trn) > 0);
+  Tmp T; float *dt = T.up(theta, (size_t)B * nth_of(rot, scl, trn)), *dA = T.dev((size_t)B * 6); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(affine_matrix_fwd(dt, dA, B, rot, scl, trn)); CG_TRY(T.down(A, dA, (size_t)B * 6)); return T.finish();
+}
+int cg_affine_matrix_bwd(const float* theta, const float* gA, float* gtheta, int B, int rot, int scl, int trn) {
+  CG_REQUIRE_INIT(); CG_ARG(theta && gA && gtheta && B > 0 && nth_of(rot, scl, trn) > 0);
+  int nth = nth_of(rot, scl, trn);
+  Tmp T; float *dt = T.up(theta, (size_t)B * nth), *dg = T.up(gA, (size_t)B * 6), *dgt = T.dev((size_t)B * nth); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(affine_matrix_bwd(dt, dg, dgt, B, rot, scl, trn)); CG_TRY(T.down(gtheta, dgt, (size_t)B * nth)); return T.finish();
+}
+int cg_affine_grid_fwd(const float* A, float* grid, int B, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(A && grid && B > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)B * H * Wd * 2; float *dA = T.up(A, (size_t)B * 6), *dg = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(affine_grid_fwd(dA, dg, B, H, Wd)); CG_TRY(T.down(grid, dg, n)); return T.finish();
+}
+int cg_affine_grid_bwd(const float* ggrid, float* gA, int B, int H, int Wd) {
+  CG_REQUIRE_INIT(); CG_ARG(ggrid && gA && B > 0 && H > 1 && Wd > 1);
+  Tmp T; size_t n = (size_t)B * H * Wd * 2; float *dg = T.up(ggrid, n), *dA = T.dev((size_t)B * 6); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(affine_grid_bwd(dg, dA, B, H, Wd)); CG_TRY(T.down(gA, dA, (size_t)B * 6)); return T.finish();
+}
+int cg_bilinear_fwd(const float* img, const float* grid, float* out, int B, int H, int Wd, int C) {
+  CG_REQUIRE_INIT(); CG_ARG(img && grid && out && B > 0 && H > 0 && Wd > 0 && C > 0);
+  Tmp T; size_t n = (size_t)B * H * Wd * C; float *di = T.up(img, n), *dg = T.up(grid, (size_t)B * H * Wd * 2), *dout = T.dev(n); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(bilinear_fwd(di, dg, dout, B, H, Wd, C)); CG_TRY(T.down(out, dout, n)); return T.finish();
+}
+int cg_bilinear_bwd(const float* img, const float* grid, const float* gout, float* gimg, float* ggrid, int B, int H, int Wd, int C) {
+  CG_REQUIRE_INIT(); CG_ARG(img && grid && gout && gimg && ggrid && B > 0 && H > 0 && Wd > 0 && C > 0);
+  Tmp T; size_t n = (size_t)B * H * Wd * C, ng = (size_t)B * H * Wd * 2;
+  float *di = T.up(img, n), *dg = T.up(grid, ng), *dgo = T.up(gout, n), *dgi = T.dev(n), *dgg = T.dev(ng); if (!T.ok) return set_err(CG_ERR_CUDA, "staging failed");
+  CG_TRY(bilinear_bwd(di, dg, dgo, dgi, dgg, B, H, Wd, C)); CG_TRY(T.down(gimg, dgi, n)); CG_TRY(T.down(ggrid, dgg, ng)); return T.finish();
+}
+
+}  // extern "C"

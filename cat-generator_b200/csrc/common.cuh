@@ -1,0 +1,101 @@
+// common.cuh -- shared infrastructure of libcatgen (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/catgen.h"
+
+namespace cg {
+
+struct Ctx {
+  int device = -1;
+  bool inited = false;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int conv_engine = 1;
+  int64_t launches = 0;
+  char err[1024] = {0};
+  // scratch (grown on demand, stream-ordered reuse)
+  void* ws = nullptr; size_t ws_bytes = 0;
+  void* ws2 = nullptr; size_t ws2_bytes = 0;
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+  // data parallel
+  int rank = 0, world = 1;
+  void* nccl = nullptr;
+};
+Ctx& ctx();
+
+int set_err(int code, const char* fmt, ...);
+void* workspace(size_t bytes);    // device scratch #1 (split-K partials, reductions)
+void* workspace2(size_t bytes);   // device scratch #2 (boundary staging / packed operands)
+void* pinned(size_t bytes);       // pinned host staging
+
+#define CG_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return cg::set_err(CG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define CG_TRY(expr) do { int _s = (expr); if (_s != CG_OK) return _s; } while (0)
+#define CG_REQUIRE_INIT() do { if (!cg::ctx().inited) return cg::set_err(CG_ERR_STATE, "cg_init has not been called"); } while (0)
+#define CG_ARG(cond) do { if (!(cond)) return cg::set_err(CG_ERR_ARG, "%s:%d argument check failed: %s", __FILE__, __LINE__, #cond); } while (0)
+
+// every kernel launch of this library goes through this macro so cg_launch_count() is exact
+#define CG_LAUNCH(kernel, grid, block, smem, ...)                                             \
+  do {                                                                                        \
+    kernel<<<(grid), (block), (smem), cg::ctx().stream>>>(__VA_ARGS__);                       \
+    cg::ctx().launches++;                                                                     \
+    cudaError_t _e = cudaPeekAtLastError();                                                   \
+    if (_e != cudaSuccess)                                                                    \
+      return cg::set_err(CG_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int grid1d(long n, int block, int per_thread = 1) {
+  long g = (n + (long)block * per_thread - 1) / ((long)block * per_thread);
+  if (g < 1) g = 1;
+  long cap = (long)ctx().sm_count * 16;   // grid-stride loops: a few waves of 148 SMs
+  return (int)(g < cap ? g : cap);
+}
+
+// growable device buffer
+struct DBuf {
+  float* p = nullptr; size_t n = 0;
+  int ensure(size_t nfloats);
+  void release();
+};
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Philox4x32-10 counter-based RNG (own implementation of the published algorithm, Salmon et al. 2011)
+__host__ __device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__host__ __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+
+}  // namespace cg

@@ -1,0 +1,279 @@
+// conv_ref.cu -- generic fp32 CUDA-core implicit-GEMM convolution over NHWC (stride 1, pad (k-1)/2) with
+// deterministic split-K, used for every shape the tcgen05 engine does not take (Cin/Cout of 1, 3, 16; Linear
+// layers run through it as 1x1 convolutions) and as the second party in the tensor-core parity tests.
+// Semantics: SURVEY.md A.1 / A.2.  Reference call sites: models.lua:145-154,199-222,646-700,844-854.
+#include "ops.cuh"
+
+namespace cg {
+
+// ------------------------------------------------------------------ parameter packing
+__device__ __forceinline__ long torch_index(int k, int Ci, int Co, int in_hw, int out_hw, int ky, int kx, int cip, int cop) {
+  if (in_hw == 1 && out_hw == 1) return (((long)cop * Ci + cip) * k + ky) * k + kx;          // conv, or plain Linear
+  int Civ = Ci / in_hw, Cov = Co / out_hw;                                                      // Linear beside an nn.View
+  int fi = (cip % Civ) * in_hw + cip / Civ;
+  int fo = (cop % Cov) * out_hw + cop / Cov;
+  return (long)fo * Ci + fi;
+}
+__global__ void k_pack_fprop(const float* __restrict__ W, float* __restrict__ Wp, long n, ConvSpec s) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
+    Wp[i] = W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)];
+  }
+}
+int pack_fprop(const float* W, float* Wp, const ConvSpec& s) {
+  long n = (long)s.k * s.k * s.Ci * s.Co; CG_LAUNCH(k_pack_fprop, grid1d(n, 256), 256, 0, W, Wp, n, s); return CG_OK;
+}
+// dgrad as a forward conv of gy: Wd[(ky,kx,co)][ci] = W[co][ci][k-1-ky][k-1-kx]
+__global__ void k_pack_dgrad(const float* __restrict__ W, float* __restrict__ Wd, long n, ConvSpec s) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % s.Ci); long r = i / s.Ci; int co = (int)(r % s.Co); int tap = (int)(r / s.Co);
+    int ky = s.k - 1 - tap / s.k, kx = s.k - 1 - tap % s.k;
+    Wd[i] = W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, ky, kx, ci, co)];
+  }
+}
+int pack_dgrad(const float* W, float* Wd, const ConvSpec& s) {
+  long n = (long)s.k * s.k * s.Ci * s.Co; CG_LAUNCH(k_pack_dgrad, grid1d(n, 256), 256, 0, W, Wd, n, s); return CG_OK;
+}
+__global__ void k_pack_bias(const float* __restrict__ b, float* __restrict__ bp, ConvSpec s, int dir, int acc) {
+  int cop = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cop >= s.Co) return;
+  int Cov = s.Co / s.out_hw;
+  int fo = s.out_hw == 1 ? cop : (cop % Cov) * s.out_hw + cop / Cov;
+  if (dir == 0) bp[cop] = b[fo];
+  else { if (acc) bp[fo] += b[cop]; else bp[fo] = b[cop]; }
+}
+int pack_bias(const float* b, float* bp, const ConvSpec& s) { CG_LAUNCH(k_pack_bias, cdiv(s.Co, 128), 128, 0, b, bp, s, 0, 0); return CG_OK; }
+int unpack_bias_acc(const float* gbp, float* gb_acc, const ConvSpec& s) { CG_LAUNCH(k_pack_bias, cdiv(s.Co, 128), 128, 0, gbp, gb_acc, s, 1, 1); return CG_OK; }
+__global__ void k_unpack_wgrad(const float* __restrict__ gWp, float* __restrict__ gW, long n, ConvSpec s) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
+    gW[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)] += gWp[i];   // accGradParameters adds
+  }
+}
+int unpack_wgrad_acc(const float* gWp, float* gW_acc, const ConvSpec& s) {
+  long n = (long)s.k * s.k * s.Ci * s.Co; CG_LAUNCH(k_unpack_wgrad, grid1d(n, 256), 256, 0, gWp, gW_acc, n, s); return CG_OK;
+}
+
+// ------------------------------------------------------------------ split-K reduction (fixed order)
+__global__ void k_splitk_reduce(const float* __restrict__ part, int S, long n, int ncol, const float* __restrict__ bias, float* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = bias ? bias[i % ncol] : 0.f;
+    for (int z = 0; z < S; ++z) s += part[(long)z * n + i];
+    out[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------ forward / dgrad: C[M=pixels, Co] = A[M, K=(tap,ci)] * Wp[K, Co]
+constexpr int BM = 64, BN = 64, BK = 16;
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_conv_fwd(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bias,
+                                                  float* __restrict__ y, long M, int H, int W, int Ci, int Co, int k, int Ktot, int Kper, int S) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  int tid = threadIdx.x;
+  long m0 = (long)blockIdx.x * BM; int n0 = blockIdx.y * BN;
+  int kbeg = blockIdx.z * Kper, kend = kbeg + Kper; if (kend > Ktot) kend = Ktot;
+  int p = (k - 1) / 2;
+  // A loader: row am, 4 consecutive kk starting at akq
+  int am = tid >> 2, akq = (tid & 3) * 4;
+  long mrow = m0 + am; bool mval = mrow < M;
+  int px = 0, py = 0; long pimg = 0;
+  if (mval) { px = (int)(mrow % W); long t = mrow / W; py = (int)(t % H); pimg = t / H; }
+  // B loader: row bk, 4 consecutive co at bc
+  int bk = tid >> 4, bc = (tid & 15) * 4;
+  int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    int kk = k0 + akq;
+    if (mval) {
+      if (VEC) {   // Ci % 4 == 0: the 4 kk share one tap and are contiguous in memory
+        if (kk < kend) {
+          int tap = kk / Ci, ci = kk - tap * Ci;
+          int iy = py + tap / k - p, ix = px + tap % k - p;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            float4 v = *reinterpret_cast<const float4*>(x + ((pimg * H + iy) * W + ix) * Ci + ci);
+            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int kj = kk + j;
+          if (kj < kend) {
+            int tap = kj / Ci, ci = kj - tap * Ci;
+            int iy = py + tap / k - p, ix = px + tap % k - p;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) av[j] = x[((pimg * H + iy) * W + ix) * Ci + ci];
+          }
+        }
+      }
+    }
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    int kb = k0 + bk;
+    if (kb < kend) {
+      const float* wr = Wp + (long)kb * Co + n0 + bc;
+      if (VEC && n0 + bc + 3 < Co) { float4 v = *reinterpret_cast<const float4*>(wr); bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w; }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n0 + bc + j < Co) bv[j] = wr[j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[akq + j][am] = av[j];
+    *reinterpret_cast<float4*>(&Bs[bk][bc]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      float4 a = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+      float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  float* out = S > 1 ? y + (long)blockIdx.z * M * Co : y;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = n0 + tx * 4 + j;
+      if (c < Co) out[m * Co + c] = acc[i][j] + ((S == 1 && bias) ? bias[c] : 0.f);
+    }
+  }
+}
+
+static int conv_fwd_ref(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
+  long M = (long)N * H * W; int Ktot = k * k * Ci;
+  int tiles = cdiv(M, BM) * cdiv(Co, BN);
+  int S = 1;
+  int target = ctx().sm_count * 2;
+  if (tiles < target) { S = target / tiles; int maxs = Ktot / (4 * BK); if (S > maxs) S = maxs; if (S < 1) S = 1; if (S > 64) S = 64; }
+  int Kper = cdiv(cdiv(Ktot, S), BK) * BK; S = cdiv(Ktot, Kper);
+  dim3 g(cdiv(M, BM), cdiv(Co, BN), S);
+  bool vec = (Ci % 4 == 0) && (Co % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)Wp & 15) == 0);
+  float* dst = y;
+  if (S > 1) { dst = (float*)workspace(sizeof(float) * (size_t)S * M * Co); if (!dst) return CG_ERR_CUDA; }
+  if (vec) CG_LAUNCH(k_conv_fwd<true>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
+  else CG_LAUNCH(k_conv_fwd<false>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
+  if (S > 1) { long n = M * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, bias, y); }
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ wgrad: gWp[K=(tap,ci), Co] = sum_m A[m, K] * gy[m, Co]
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_conv_wgrad(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ out,
+                                                    long M, int H, int W, int Ci, int Co, int k, int Ktot, long Mper) {
+  __shared__ __align__(16) float As[BK][BM];   // [m chunk][kk]
+  __shared__ __align__(16) float Gs[BK][BN];   // [m chunk][co]
+  int tid = threadIdx.x;
+  int kk0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  long mbeg = (long)blockIdx.z * Mper, mend = mbeg + Mper; if (mend > M) mend = M;
+  int p = (k - 1) / 2;
+  int lm = tid >> 4, lq = (tid & 15) * 4;   // loaders: row lm of the chunk, 4 consecutive kk / co
+  int ty = tid >> 4, tx = tid & 15;
+  // per-thread tap decode for its 4 kk (fixed for the whole kernel)
+  int tap4[4], ci4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { int kj = kk0 + lq + j; tap4[j] = kj < Ktot ? kj / Ci : -1; ci4[j] = kj < Ktot ? kj % Ci : 0; }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long mc = mbeg; mc < mend; mc += BK) {
+    long m = mc + lm;
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < mend) {
+      int px = (int)(m % W); long t = m / W; int py = (int)(t % H); long pimg = t / H;
+      if (VEC) {
+        if (tap4[0] >= 0) {
+          int iy = py + tap4[0] / k - p, ix = px + tap4[0] % k - p;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            float4 v = *reinterpret_cast<const float4*>(x + ((pimg * H + iy) * W + ix) * Ci + ci4[0]);
+            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (tap4[j] >= 0) {
+          int iy = py + tap4[j] / k - p, ix = px + tap4[j] % k - p;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) av[j] = x[((pimg * H + iy) * W + ix) * Ci + ci4[j]];
+        }
+      }
+      const float* gr = gy + m * Co + n0 + lq;
+      if (VEC && n0 + lq + 3 < Co) { float4 v = *reinterpret_cast<const float4*>(gr); gv[0] = v.x; gv[1] = v.y; gv[2] = v.z; gv[3] = v.w; }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n0 + lq + j < Co) gv[j] = gr[j];
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lm][lq]) = make_float4(av[0], av[1], av[2], av[3]);
+    *reinterpret_cast<float4*>(&Gs[lm][lq]) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      float4 a = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Gs[q][tx * 4]);
+      float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  float* o = out + (long)blockIdx.z * Ktot * Co;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kk = kk0 + ty * 4 + i;
+    if (kk >= Ktot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { int c = n0 + tx * 4 + j; if (c < Co) o[(long)kk * Co + c] = acc[i][j]; }
+  }
+}
+
+static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
+  long M = (long)N * H * W; int Ktot = k * k * Ci;
+  int tiles = cdiv(Ktot, BM) * cdiv(Co, BN);
+  int target = ctx().sm_count * 3;
+  int S = cdiv(target, tiles); long maxs = (M + 4 * BK - 1) / (4 * BK); if (S > maxs) S = (int)maxs; if (S < 1) S = 1; if (S > 256) S = 256;
+  long Mper = ((M + S - 1) / S + BK - 1) / BK * BK; S = (int)((M + Mper - 1) / Mper);
+  dim3 g(cdiv(Ktot, BM), cdiv(Co, BN), S);
+  bool vec = (Ci % 4 == 0) && (Co % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)gy & 15) == 0);
+  float* dst = gWp_out;
+  if (S > 1) { dst = (float*)workspace(sizeof(float) * (size_t)S * Ktot * Co); if (!dst) return CG_ERR_CUDA; }
+  if (vec) CG_LAUNCH(k_conv_wgrad<true>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
+  else CG_LAUNCH(k_conv_wgrad<false>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
+  if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out); }
+  return CG_OK;
+}
+
+// ------------------------------------------------------------------ engine dispatch
+// conv_tc.cu provides these; they return CG_ERR_UNSUPPORTED for shapes the tensor-core path does not take.
+int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+
+int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
+  if (ctx().conv_engine == 1) { int s = conv_fwd_tc(x, Wp, bias, y, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
+  return conv_fwd_ref(x, Wp, bias, y, N, H, W, Ci, Co, k);
+}
+int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k) {
+  // dgrad is a forward convolution of gy (Co channels) with the flipped/transposed weights
+  return conv_fwd(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k);
+}
+int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
+  if (ctx().conv_engine == 1) { int s = conv_wgrad_tc(x, gy, gWp_out, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
+  return conv_wgrad_ref(x, gy, gWp_out, N, H, W, Ci, Co, k);
+}
+
+}  // namespace cg

@@ -1,0 +1,418 @@
+// model.cu -- G / D executors.  Layer graphs follow models.lua:138-160 (G32up), :196-228 (G32up-c),
+// :640-711 (D32_st3) and :814-906 (spatial transformer); initialisation follows weight-init.lua:40-75 and the
+// nn defaults.
+#include "model.cuh"
+#include <math.h>
+
+namespace cg {
+
+static float* FW(cg_model* m, size_t n) {
+  if ((int)m->fw.size() <= m->nfw) m->fw.resize(m->nfw + 16);
+  DBuf& b = m->fw[m->nfw++];
+  return b.ensure(n) == CG_OK ? b.p : nullptr;
+}
+static float* BW(cg_model* m, size_t n) {
+  if ((int)m->bw.size() <= m->nbw) m->bw.resize(m->nbw + 16);
+  DBuf& b = m->bw[m->nbw++];
+  return b.ensure(n) == CG_OK ? b.p : nullptr;
+}
+#define NN(p) do { if (!(p)) return cg::set_err(CG_ERR_CUDA, "%s:%d device allocation failed", __FILE__, __LINE__); } while (0)
+
+static int add_layer(cg_model* m, int Ci, int Co, int k, long& o, int in_hw = 1, int out_hw = 1, bool need_dgrad = true) {
+  cg_layer L; L.s.Ci = Ci; L.s.Co = Co; L.s.k = k; L.s.in_hw = in_hw; L.s.out_hw = out_hw; L.need_dgrad = need_dgrad;
+  L.oW = o; o += (long)Co * Ci * k * k; L.ob = o; o += Co;
+  m->layers.push_back(L);
+  return (int)m->layers.size() - 1;
+}
+static long stn_layout(cg_model* m, cg_stn* s, long o, int ch, int S, int rot, int scl, int trn, bool first) {
+  s->ch = ch; s->S = S; s->rot = rot; s->scl = scl; s->trn = trn; s->nth = (rot ? 1 : 0) + (scl ? 1 : 0) + (trn ? 2 : 0);
+  int S4 = S / 4;
+  // nn has no "needs input grad" switch: dgrad is computed for every layer incl. the first
+  (void)first;
+  s->c1 = add_layer(m, ch, 16, 3, o);
+  s->c2 = add_layer(m, 16, 16, 3, o);
+  s->l1 = add_layer(m, 16 * S4 * S4, 64, 1, o, S4 * S4, 1);
+  s->l2 = add_layer(m, 64, s->nth, 1, o);
+  return o;
+}
+
+long D_mask_floats(int B) { return (long)B * (64 * 4 + 128 + 320 + 256); }
+
+static int init_uniform(cg_model* m, long off, long n, float lo, float hi) {
+  int s = uniform(m->P + off, n, lo, hi, m->seed, m->rng_offset);
+  m->rng_offset += (uint64_t)(n + 3) / 4 + 1;
+  return s;
+}
+static int init_layer(cg_model* m, int li, bool random_bias) {
+  cg_layer& L = m->layers[li];
+  long nW = (long)L.s.Co * L.s.Ci * L.s.k * L.s.k;
+  float sd = 1.f / sqrtf((float)L.s.Ci * L.s.k * L.s.k);
+  CG_TRY(init_uniform(m, L.oW, nW, -sd, sd));
+  if (random_bias) CG_TRY(init_uniform(m, L.ob, L.s.Co, -sd, sd));
+  else CG_TRY(fill(m->P + L.ob, 0.f, L.s.Co));
+  return CG_OK;
+}
+static int init_stn(cg_model* m, cg_stn* s) {   // models.lua:843-860
+  CG_TRY(init_layer(m, s->c1, false)); CG_TRY(init_layer(m, s->c2, false)); CG_TRY(init_layer(m, s->l1, false));
+  cg_layer& L = m->layers[s->l2];
+  CG_TRY(fill(m->P + L.oW, 0.f, (long)s->nth * 64));
+  float b[4] = {0, 0, 0, 0}; int q = 0;
+  if (s->rot) b[q++] = 0.f;
+  if (s->scl) b[q++] = 1.f;
+  if (s->trn) { b[q++] = 0.f; b[q++] = 0.f; }
+  CG_CUDA(cudaMemcpyAsync(m->P + L.ob, b, sizeof(float) * s->nth, cudaMemcpyHostToDevice, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream));   // b is a stack array
+  return CG_OK;
+}
+
+int model_build(cg_model* m) {
+  long o = 0; int C = m->C;
+  if (m->kind == CG_G32UP || m->kind == CG_G32UPC) {
+    if (m->kind == CG_G32UPC) {
+      m->C0 = 512; m->s0 = 4; m->nst = 4;
+      cg_gstage s[4] = {{1, 512, 512, 3, 1}, {1, 512, 256, 3, 1}, {1, 256, 128, 5, 1}, {0, 128, C, 3, 0}};
+      memcpy(m->st, s, sizeof(s));
+    } else {
+      m->C0 = 128; m->s0 = 8; m->nst = 3;
+      cg_gstage s[3] = {{1, 128, 256, 5, 1}, {1, 256, 128, 5, 1}, {0, 128, C, 3, 0}};
+      memcpy(m->st, s, sizeof(s));
+    }
+    int hw0 = m->s0 * m->s0;
+    m->lin_layer = add_layer(m, m->nz, m->C0 * hw0, 1, o, 1, hw0);
+    m->oLpw = o; o += 1;
+    m->nrun = 0;
+    for (int i = 0; i < m->nst; ++i) {
+      cg_gstage& s = m->st[i];
+      s.layer = add_layer(m, s.Ci, s.Co, s.k, o);
+      if (s.bn) { s.og = o; o += s.Co; s.obt = o; o += s.Co; s.opw = o; o += 1; m->nrun += 2 * s.Co; }
+    }
+  } else if (m->kind == CG_D32_ST3) {
+    o = stn_layout(m, &m->stn[0], o, C, 32, 1, 0, 0, true);
+    m->t1 = add_layer(m, C, 64, 3, o); m->t1pw = o; o += 1;
+    m->t2 = add_layer(m, 64, 64, 3, o); m->t2pw = o; o += 1;
+    for (int b = 0; b < 3; ++b) {
+      o = stn_layout(m, &m->stn[b + 1], o, 64, 16, 1, 1, 1, false);
+      m->b1[b] = add_layer(m, 64, 64, 3, o); m->bpw1[b] = o; o += 1;
+      m->b2[b] = add_layer(m, 64, 64, 3, o); m->bpw2[b] = o; o += 1;
+    }
+    m->b1[3] = add_layer(m, 64, 128, 5, o); m->bpw1[3] = o; o += 1;
+    m->b2[3] = add_layer(m, 128, 128, 7, o); m->bpw2[3] = o; o += 1;
+    m->h1 = add_layer(m, 20480, 256, 1, o, 64, 1); m->hpw = o; o += 1;
+    m->h2 = add_layer(m, 256, 1, 1, o);
+  } else return set_err(CG_ERR_ARG, "unknown model kind %d", m->kind);
+  m->np = o;
+  CG_CUDA(cudaMalloc(&m->P, sizeof(float) * o));
+  CG_CUDA(cudaMalloc(&m->G, sizeof(float) * o));
+  CG_CUDA(cudaMemsetAsync(m->G, 0, sizeof(float) * o, ctx().stream));
+  // packed operands: Wp, Wd, bp per layer, each 16-byte aligned
+  size_t pf = 0;
+  for (auto& L : m->layers) { size_t nW = (size_t)L.s.Co * L.s.Ci * L.s.k * L.s.k; pf += 2 * ((nW + 3) & ~(size_t)3) + (((size_t)L.s.Co + 3) & ~(size_t)3); }
+  m->packed_floats = pf;
+  CG_CUDA(cudaMalloc(&m->packed, sizeof(float) * pf));
+  size_t q = 0; size_t maxW = 0;
+  for (auto& L : m->layers) {
+    size_t nW = (size_t)L.s.Co * L.s.Ci * L.s.k * L.s.k, nWa = (nW + 3) & ~(size_t)3;
+    L.Wp = m->packed + q; q += nWa; L.Wd = m->packed + q; q += nWa; L.bp = m->packed + q; q += ((size_t)L.s.Co + 3) & ~(size_t)3;
+    if (nW > maxW) maxW = nW;
+  }
+  CG_TRY(m->gwp.ensure(maxW + 32768));
+  if (m->nrun) {
+    CG_CUDA(cudaMalloc(&m->run, sizeof(float) * m->nrun));
+    long r = 0;
+    for (int i = 0; i < m->nst; ++i) if (m->st[i].bn) {
+      CG_TRY(fill(m->run + r, 0.f, m->st[i].Co)); CG_TRY(fill(m->run + r + m->st[i].Co, 1.f, m->st[i].Co)); r += 2 * m->st[i].Co;
+    }
+  }
+  // ---- initialisation (distribution parity only; parity tests exchange parameters as data)
+  const float quarter = 0.25f;
+  auto set_scalar = [&](long off, float v) -> int { return fill(m->P + off, v, 1); };
+  if (m->kind != CG_D32_ST3) {
+    CG_TRY(init_layer(m, m->lin_layer, false)); CG_TRY(set_scalar(m->oLpw, quarter));
+    for (int i = 0; i < m->nst; ++i) {
+      cg_gstage& s = m->st[i];
+      CG_TRY(init_layer(m, s.layer, false));   // weight-init.lua:70-72 zeroes the bias of every top-level module
+      if (s.bn) { CG_TRY(init_uniform(m, s.og, s.Co, 0.f, 1.f)); CG_TRY(fill(m->P + s.obt, 0.f, s.Co)); CG_TRY(set_scalar(s.opw, quarter)); }
+    }
+  } else {
+    CG_TRY(init_stn(m, &m->stn[0]));
+    CG_TRY(init_layer(m, m->t1, false)); CG_TRY(set_scalar(m->t1pw, quarter));
+    CG_TRY(init_layer(m, m->t2, false)); CG_TRY(set_scalar(m->t2pw, quarter));
+    for (int b = 0; b < 4; ++b) {
+      if (b < 3) CG_TRY(init_stn(m, &m->stn[b + 1]));
+      // nested inside nn.Concat => untouched by weight-init: nn default reset(), random bias
+      CG_TRY(init_layer(m, m->b1[b], true)); CG_TRY(set_scalar(m->bpw1[b], quarter));
+      CG_TRY(init_layer(m, m->b2[b], true)); CG_TRY(set_scalar(m->bpw2[b], quarter));
+    }
+    CG_TRY(init_layer(m, m->h1, false)); CG_TRY(set_scalar(m->hpw, quarter));
+    CG_TRY(init_layer(m, m->h2, false));
+  }
+  m->dirty = true;
+  return CG_OK;
+}
+
+int model_repack(cg_model* m) {
+  if (!m->dirty) return CG_OK;
+  for (auto& L : m->layers) {
+    CG_TRY(pack_fprop(m->P + L.oW, L.Wp, L.s));
+    if (L.need_dgrad) CG_TRY(pack_dgrad(m->P + L.oW, L.Wd, L.s));
+    CG_TRY(pack_bias(m->P + L.ob, L.bp, L.s));
+  }
+  m->dirty = false;
+  return CG_OK;
+}
+
+// x: [N,H,W,Ci] -> y: [N,H,W,Co]
+static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H, int W) {
+  cg_layer& L = m->layers[li];
+  return conv_fwd(x, L.Wp, L.bp, y, N, H, W, L.s.Ci, L.s.Co, L.s.k);
+}
+// accumulates dW, db into the flat gradient; gx may be null
+static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W) {
+  cg_layer& L = m->layers[li];
+  long M = (long)N * H * W;
+  CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k));
+  CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
+  if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
+  else {
+    float* tmp = m->gwp.p;   // wgrad scratch is free again (stream ordered)
+    CG_TRY(fill(tmp, 0.f, L.s.Co)); CG_TRY(colsum_acc(gy, tmp, M, L.s.Co)); CG_TRY(unpack_bias_acc(tmp, m->G + L.ob, L.s));
+  }
+  if (gx) CG_TRY(conv_dgrad(gy, L.Wd, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k));
+  return CG_OK;
+}
+
+// =================================================================== G
+int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
+  CG_TRY(model_repack(g));
+  g->nfw = 0; g->B = B;
+  long F0 = (long)g->C0 * g->s0 * g->s0;
+  float* zc = FW(g, (size_t)B * g->nz); NN(zc);
+  CG_CUDA(cudaMemcpyAsync(zc, z_dev, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, ctx().stream));
+  g->z = zc;
+  g->lin = FW(g, B * F0); g->act0 = FW(g, B * F0); NN(g->lin); NN(g->act0);
+  CG_TRY(layer_fwd(g, g->lin_layer, zc, g->lin, B, 1, 1));            // nn.Linear(nz, C0*s0*s0); output already NHWC
+  CG_TRY(prelu_fwd(g->lin, g->P + g->oLpw, g->act0, B * F0));
+  const float* cur = g->act0; int h = g->s0; long r = 0;
+  for (int i = 0; i < g->nst; ++i) {
+    cg_gstage& s = g->st[i];
+    if (s.up) {
+      g->sup[i] = FW(g, (size_t)B * 4 * h * h * s.Ci); NN(g->sup[i]);
+      CG_TRY(upsample2x_fwd(cur, g->sup[i], B, h, h, s.Ci));
+      h *= 2; cur = g->sup[i];
+    } else g->sup[i] = (float*)cur;
+    long M = (long)B * h * h, no = M * s.Co;
+    g->sconv[i] = FW(g, no); NN(g->sconv[i]);
+    CG_TRY(layer_fwd(g, s.layer, cur, g->sconv[i], B, h, h));
+    g->sact[i] = FW(g, no); NN(g->sact[i]);
+    if (s.bn) {
+      g->sbn[i] = FW(g, no); g->smean[i] = FW(g, s.Co); g->sinv[i] = FW(g, s.Co); NN(g->sbn[i]); NN(g->smean[i]); NN(g->sinv[i]);
+      if (g->training)   // adversarial.train never switches G to evaluate(): batch statistics
+        CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
+      else
+        CG_TRY(bn_fwd_eval(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f));
+      r += 2 * s.Co;
+      CG_TRY(prelu_fwd(g->sbn[i], g->P + s.opw, g->sact[i], no));
+    } else CG_TRY(sigmoid_fwd(g->sconv[i], g->sact[i], no));
+    cur = g->sact[i];
+  }
+  CG_TRY(nhwc_to_nchw(cur, out_nchw, B, g->C, 32 * 32));
+  return CG_OK;
+}
+
+int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
+  if (!g->B) return set_err(CG_ERR_STATE, "G backward before forward");
+  if (!g->training) return set_err(CG_ERR_STATE, "G backward needs a training-mode forward (batch-stat BN)");
+  g->nbw = 0; int B = g->B, h = 32;
+  float* gcur = BW(g, (size_t)B * g->C * 1024); NN(gcur);
+  CG_TRY(nchw_to_nhwc(gout_nchw, gcur, B, g->C, 1024));
+  for (int i = g->nst - 1; i >= 0; --i) {
+    cg_gstage& s = g->st[i];
+    long M = (long)B * h * h, no = M * s.Co;
+    float* gconv = BW(g, no); NN(gconv);
+    if (s.bn) {
+      float* gbn = BW(g, no); NN(gbn);
+      CG_TRY(prelu_bwd(g->sbn[i], gcur, g->P + s.opw, gbn, g->G + s.opw, no));
+      CG_TRY(bn_bwd(g->sconv[i], gbn, g->P + s.og, g->smean[i], g->sinv[i], gconv, g->G + s.og, g->G + s.obt, M, s.Co));
+    } else CG_TRY(sigmoid_bwd(g->sact[i], gcur, gconv, no));
+    float* gin = BW(g, (size_t)M * s.Ci); NN(gin);
+    CG_TRY(layer_bwd(g, s.layer, g->sup[i], gconv, gin, B, h, h));
+    if (s.up) {
+      h /= 2;
+      float* gs = BW(g, (size_t)B * h * h * s.Ci); NN(gs);
+      CG_TRY(upsample2x_bwd(gin, gs, B, h, h, s.Ci));
+      gin = gs;
+    }
+    gcur = gin;
+  }
+  long F0 = (long)g->C0 * g->s0 * g->s0;
+  float* glin = BW(g, B * F0); NN(glin);
+  CG_TRY(prelu_bwd(g->lin, gcur, g->P + g->oLpw, glin, g->G + g->oLpw, B * F0));
+  float* gz = gz_dev ? gz_dev : BW(g, (size_t)B * g->nz); NN(gz);
+  CG_TRY(layer_bwd(g, g->lin_layer, g->z, glin, gz, B, 1, 1));
+  return CG_OK;
+}
+
+// =================================================================== D
+__global__ void k_copy_channels(const float* __restrict__ src, float* __restrict__ dst, long n, int Cs, int Cd, int coff, int dir) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long r = i / Cs; int c = (int)(i % Cs);
+    if (dir == 0) dst[r * Cd + coff + c] = src[i];        // nn.Concat(2) forward: into the channel slot
+    else dst[i] = src[r * Cd + coff + c];                  // backward: slice of gradOutput
+  }
+}
+static int copy_channels(const float* src, float* dst, long rows, int Cs, int Cd, int coff, int dir) {
+  long n = rows * Cs; CG_LAUNCH(k_copy_channels, grid1d(n, 256, 4), 256, 0, src, dst, n, Cs, Cd, coff, dir); return CG_OK;
+}
+
+static int stn_forward(cg_model* m, cg_stn* s, const float* in, int B) {
+  int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
+  s->in = in;
+  s->pool1 = FW(m, (size_t)B * S2 * S2 * ch); NN(s->pool1); CG_TRY(avgpool2_fwd(in, s->pool1, B, S, S, ch));
+  long n2 = (long)B * S2 * S2 * 16;
+  s->c1o = FW(m, n2); s->a1 = FW(m, n2); s->c2o = FW(m, n2); s->a2 = FW(m, n2); NN(s->c1o); NN(s->a1); NN(s->c2o); NN(s->a2);
+  CG_TRY(layer_fwd(m, s->c1, s->pool1, s->c1o, B, S2, S2)); CG_TRY(lrelu_fwd(s->c1o, 0.333f, s->a1, n2));
+  CG_TRY(layer_fwd(m, s->c2, s->a1, s->c2o, B, S2, S2)); CG_TRY(lrelu_fwd(s->c2o, 0.333f, s->a2, n2));
+  s->pool2 = FW(m, (size_t)B * f); NN(s->pool2); CG_TRY(avgpool2_fwd(s->a2, s->pool2, B, S2, S2, 16));
+  s->l1o = FW(m, (size_t)B * 64); s->al1 = FW(m, (size_t)B * 64); NN(s->l1o); NN(s->al1);
+  CG_TRY(layer_fwd(m, s->l1, s->pool2, s->l1o, B, 1, 1)); CG_TRY(lrelu_fwd(s->l1o, 0.333f, s->al1, (long)B * 64));
+  s->theta = FW(m, (size_t)B * 4); NN(s->theta); CG_TRY(layer_fwd(m, s->l2, s->al1, s->theta, B, 1, 1));
+  s->A = FW(m, (size_t)B * 6); NN(s->A); CG_TRY(affine_matrix_fwd(s->theta, s->A, B, s->rot, s->scl, s->trn));
+  s->grid = FW(m, (size_t)B * S * S * 2); NN(s->grid); CG_TRY(affine_grid_fwd(s->A, s->grid, B, S, S));
+  s->out = FW(m, (size_t)B * S * S * ch); NN(s->out); CG_TRY(bilinear_fwd(in, s->grid, s->out, B, S, S, ch));
+  return CG_OK;
+}
+// gout, gin: [B,S,S,ch]; gin is written (sum of the sampler branch and the localisation branch, nn.ConcatTable)
+static int stn_backward(cg_model* m, cg_stn* s, const float* gout, float* gin, int B) {
+  int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
+  float* ggrid = BW(m, (size_t)B * S * S * 2); NN(ggrid);
+  CG_TRY(bilinear_bwd(s->in, s->grid, gout, gin, ggrid, B, S, S, ch));
+  float* gA = BW(m, (size_t)B * 6); NN(gA); CG_TRY(affine_grid_bwd(ggrid, gA, B, S, S));
+  float* gth = BW(m, (size_t)B * 4); NN(gth); CG_TRY(affine_matrix_bwd(s->theta, gA, gth, B, s->rot, s->scl, s->trn));
+  float* gal1 = BW(m, (size_t)B * 64); NN(gal1); CG_TRY(layer_bwd(m, s->l2, s->al1, gth, gal1, B, 1, 1));
+  float* gl1 = BW(m, (size_t)B * 64); NN(gl1); CG_TRY(lrelu_bwd(s->l1o, gal1, 0.333f, gl1, (long)B * 64));
+  float* gp2 = BW(m, (size_t)B * f); NN(gp2); CG_TRY(layer_bwd(m, s->l1, s->pool2, gl1, gp2, B, 1, 1));
+  long n2 = (long)B * S2 * S2 * 16;
+  float* ga2 = BW(m, n2); NN(ga2); CG_TRY(avgpool2_bwd(gp2, ga2, B, S2, S2, 16));
+  float* gc2 = BW(m, n2); NN(gc2); CG_TRY(lrelu_bwd(s->c2o, ga2, 0.333f, gc2, n2));
+  float* ga1 = BW(m, n2); NN(ga1); CG_TRY(layer_bwd(m, s->c2, s->a1, gc2, ga1, B, S2, S2));
+  float* gc1 = BW(m, n2); NN(gc1); CG_TRY(lrelu_bwd(s->c1o, ga1, 0.333f, gc1, n2));
+  float* gp1 = BW(m, (size_t)B * S2 * S2 * ch); NN(gp1); CG_TRY(layer_bwd(m, s->c1, s->pool1, gc1, gp1, B, S2, S2));
+  float* gin2 = BW(m, (size_t)B * S * S * ch); NN(gin2); CG_TRY(avgpool2_bwd(gp1, gin2, B, S, S, ch));
+  CG_TRY(add_inplace(gin, gin2, (long)B * S * S * ch));
+  return CG_OK;
+}
+
+static int ensure_masks(cg_model* d, int B) {
+  long n = D_mask_floats(B);
+  if (d->masks_n < n) { if (d->masks) { cudaStreamSynchronize(ctx().stream); cudaFree(d->masks); } CG_CUDA(cudaMalloc(&d->masks, sizeof(float) * n)); d->masks_n = n; }
+  d->masks_B = B;
+  if (d->mq && d->mq_next < d->mq_count) {   // masks queued by cg_D_set_masks: one set per forward, in order
+    if (d->mq_B != B) return set_err(CG_ERR_ARG, "queued dropout masks are for batch %d, forward has batch %d", d->mq_B, B);
+    CG_CUDA(cudaMemcpyAsync(d->masks, d->mq + (size_t)n * d->mq_next, sizeof(float) * n, cudaMemcpyDeviceToDevice, ctx().stream));
+    d->mq_next++;
+    return CG_OK;
+  }
+  long nsp = (long)B * (64 * 4 + 128), nh = (long)B * 320, nf = (long)B * 256;
+  if (d->training) {   // nn.SpatialDropout(0.2) x5 (no rescale), SpatialDropout(0.5), nn.Dropout(0.5) v2 (x2) -- SURVEY.md A.12
+    CG_TRY(bernoulli_mask(d->masks, nsp, 0.2f, 1.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nsp + 3) / 4 + 1;
+    CG_TRY(bernoulli_mask(d->masks + nsp, nh, 0.5f, 1.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nh + 3) / 4 + 1;
+    CG_TRY(bernoulli_mask(d->masks + nsp + nh, nf, 0.5f, 2.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nf + 3) / 4 + 1;
+  } else {             // evaluate(): SpatialDropout scales by (1-p); Dropout v2 is the identity
+    CG_TRY(fill(d->masks, 0.8f, nsp)); CG_TRY(fill(d->masks + nsp, 0.5f, nh)); CG_TRY(fill(d->masks + nsp + nh, 1.f, nf));
+  }
+  return CG_OK;
+}
+
+int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float* pre_dev) {
+  CG_TRY(model_repack(d));
+  CG_TRY(ensure_masks(d, B));
+  d->nfw = 0; d->B = B; int C = d->C;
+  const float* mk = d->masks;
+  d->xin = FW(d, (size_t)B * 1024 * C); NN(d->xin);
+  CG_TRY(nchw_to_nhwc(x_nchw, d->xin, B, C, 1024));                      // nn.Copy + the STN's nn.Transpose (models.lua:643,870)
+  CG_TRY(stn_forward(d, &d->stn[0], d->xin, B));
+  long n64 = (long)B * 1024 * 64;
+  d->tc1 = FW(d, n64); d->ta1 = FW(d, n64); d->tc2 = FW(d, n64); d->ta2 = FW(d, n64); NN(d->tc1); NN(d->ta1); NN(d->tc2); NN(d->ta2);
+  CG_TRY(layer_fwd(d, d->t1, d->stn[0].out, d->tc1, B, 32, 32)); CG_TRY(prelu_fwd(d->tc1, d->P + d->t1pw, d->ta1, n64));
+  CG_TRY(layer_fwd(d, d->t2, d->ta1, d->tc2, B, 32, 32)); CG_TRY(prelu_fwd(d->tc2, d->P + d->t2pw, d->ta2, n64));
+  d->tpool = FW(d, n64 / 4); d->T = FW(d, n64 / 4); NN(d->tpool); NN(d->T);
+  CG_TRY(avgpool2_fwd(d->ta2, d->tpool, B, 32, 32, 64));
+  CG_TRY(mask_channels(d->tpool, mk, d->T, B, 256, 64)); mk += (long)B * 64;
+  d->cat = FW(d, (size_t)B * 64 * 320); NN(d->cat);
+  for (int b = 0; b < 4; ++b) {
+    int Co = b < 3 ? 64 : 128;
+    const float* bin = d->T;
+    if (b < 3) { CG_TRY(stn_forward(d, &d->stn[b + 1], d->T, B)); bin = d->stn[b + 1].out; }
+    long n1 = (long)B * 256 * Co;
+    d->bc1[b] = FW(d, n1); d->ba1[b] = FW(d, n1); NN(d->bc1[b]); NN(d->ba1[b]);
+    CG_TRY(layer_fwd(d, d->b1[b], bin, d->bc1[b], B, 16, 16)); CG_TRY(prelu_fwd(d->bc1[b], d->P + d->bpw1[b], d->ba1[b], n1));
+    d->bmp[b] = FW(d, n1 / 4); d->bidx[b] = (uint8_t*)FW(d, n1 / 16 + 4); d->bdr[b] = FW(d, n1 / 4); d->bc2[b] = FW(d, n1 / 4);
+    NN(d->bmp[b]); NN(d->bidx[b]); NN(d->bdr[b]); NN(d->bc2[b]);
+    CG_TRY(maxpool2_fwd(d->ba1[b], d->bmp[b], d->bidx[b], B, 16, 16, Co));
+    CG_TRY(mask_channels(d->bmp[b], mk, d->bdr[b], B, 64, Co)); mk += (long)B * Co;
+    CG_TRY(layer_fwd(d, d->b2[b], d->bdr[b], d->bc2[b], B, 8, 8));
+    float* tmp = FW(d, n1 / 4); NN(tmp);
+    CG_TRY(prelu_fwd(d->bc2[b], d->P + d->bpw2[b], tmp, n1 / 4));
+    CG_TRY(copy_channels(tmp, d->cat, (long)B * 64, Co, 320, b * 64, 0));
+  }
+  d->catd = FW(d, (size_t)B * 20480); NN(d->catd);
+  CG_TRY(mask_channels(d->cat, mk, d->catd, B, 64, 320)); mk += (long)B * 320;
+  d->h1o = FW(d, (size_t)B * 256); d->ha1 = FW(d, (size_t)B * 256); d->hd = FW(d, (size_t)B * 256); NN(d->h1o); NN(d->ha1); NN(d->hd);
+  CG_TRY(layer_fwd(d, d->h1, d->catd, d->h1o, B, 1, 1));
+  CG_TRY(prelu_fwd(d->h1o, d->P + d->hpw, d->ha1, (long)B * 256));
+  CG_TRY(mask_elems(d->ha1, mk, d->hd, (long)B * 256));
+  d->h2o = FW(d, B); d->hsig = FW(d, B); NN(d->h2o); NN(d->hsig);
+  CG_TRY(layer_fwd(d, d->h2, d->hd, d->h2o, B, 1, 1));
+  CG_TRY(sigmoid_fwd(d->h2o, d->hsig, B));
+  if (sig_dev) CG_CUDA(cudaMemcpyAsync(sig_dev, d->hsig, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
+  if (pre_dev) CG_CUDA(cudaMemcpyAsync(pre_dev, d->h2o, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
+  return CG_OK;
+}
+
+int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
+  if (!d->B) return set_err(CG_ERR_STATE, "D backward before forward");
+  d->nbw = 0; int B = d->B, C = d->C;
+  const float* mk_trunk = d->masks;
+  const float* mk_br = d->masks + (long)B * 64;
+  const float* mk_head = d->masks + (long)B * (64 * 4 + 128);
+  const float* mk_fc = mk_head + (long)B * 320;
+  float* gh2 = BW(d, B); NN(gh2); CG_TRY(sigmoid_bwd(d->hsig, gout_dev, gh2, B));
+  float* ghd = BW(d, (size_t)B * 256); NN(ghd); CG_TRY(layer_bwd(d, d->h2, d->hd, gh2, ghd, B, 1, 1));
+  float* gha1 = BW(d, (size_t)B * 256); NN(gha1); CG_TRY(mask_elems(ghd, mk_fc, gha1, (long)B * 256));
+  float* gh1 = BW(d, (size_t)B * 256); NN(gh1); CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, d->G + d->hpw, (long)B * 256));
+  float* gcatd = BW(d, (size_t)B * 20480); NN(gcatd); CG_TRY(layer_bwd(d, d->h1, d->catd, gh1, gcatd, B, 1, 1));
+  float* gcat = BW(d, (size_t)B * 20480); NN(gcat); CG_TRY(mask_channels(gcatd, mk_head, gcat, B, 64, 320));
+  long nT = (long)B * 256 * 64;
+  float* gT = BW(d, nT); NN(gT); CG_TRY(fill(gT, 0.f, nT));
+  const float* mk = mk_br;
+  for (int b = 0; b < 4; ++b) {
+    int Co = b < 3 ? 64 : 128;
+    long n2 = (long)B * 64 * Co, n1 = n2 * 4;
+    float* go = BW(d, n2); NN(go); CG_TRY(copy_channels(gcat, go, (long)B * 64, Co, 320, b * 64, 1));
+    float* gc2 = BW(d, n2); NN(gc2); CG_TRY(prelu_bwd(d->bc2[b], go, d->P + d->bpw2[b], gc2, d->G + d->bpw2[b], n2));
+    float* gdr = BW(d, n2); NN(gdr); CG_TRY(layer_bwd(d, d->b2[b], d->bdr[b], gc2, gdr, B, 8, 8));
+    float* gmp = BW(d, n2); NN(gmp); CG_TRY(mask_channels(gdr, mk, gmp, B, 64, Co)); mk += (long)B * Co;
+    float* ga1 = BW(d, n1); NN(ga1); CG_TRY(maxpool2_bwd(gmp, d->bidx[b], ga1, B, 16, 16, Co));
+    float* gc1 = BW(d, n1); NN(gc1); CG_TRY(prelu_bwd(d->bc1[b], ga1, d->P + d->bpw1[b], gc1, d->G + d->bpw1[b], n1));
+    const float* bin = b < 3 ? d->stn[b + 1].out : d->T;
+    float* gbin = BW(d, nT); NN(gbin); CG_TRY(layer_bwd(d, d->b1[b], bin, gc1, gbin, B, 16, 16));
+    if (b < 3) {
+      float* gs = BW(d, nT); NN(gs);
+      CG_TRY(stn_backward(d, &d->stn[b + 1], gbin, gs, B));
+      CG_TRY(add_inplace(gT, gs, nT));
+    } else CG_TRY(add_inplace(gT, gbin, nT));
+  }
+  float* gtp = BW(d, nT); NN(gtp); CG_TRY(mask_channels(gT, mk_trunk, gtp, B, 256, 64));
+  long n64 = (long)B * 1024 * 64;
+  float* gta2 = BW(d, n64); NN(gta2); CG_TRY(avgpool2_bwd(gtp, gta2, B, 32, 32, 64));
+  float* gtc2 = BW(d, n64); NN(gtc2); CG_TRY(prelu_bwd(d->tc2, gta2, d->P + d->t2pw, gtc2, d->G + d->t2pw, n64));
+  float* gta1 = BW(d, n64); NN(gta1); CG_TRY(layer_bwd(d, d->t2, d->ta1, gtc2, gta1, B, 32, 32));
+  float* gtc1 = BW(d, n64); NN(gtc1); CG_TRY(prelu_bwd(d->tc1, gta1, d->P + d->t1pw, gtc1, d->G + d->t1pw, n64));
+  float* gs0 = BW(d, (size_t)B * 1024 * C); NN(gs0); CG_TRY(layer_bwd(d, d->t1, d->stn[0].out, gtc1, gs0, B, 32, 32));
+  float* gin = BW(d, (size_t)B * 1024 * C); NN(gin);
+  CG_TRY(stn_backward(d, &d->stn[0], gs0, gin, B));
+  if (gx_nchw) CG_TRY(nhwc_to_nchw(gin, gx_nchw, B, C, 1024));        // MODEL_D.modules[1].gradInput (adversarial.lua:193)
+  return CG_OK;
+}
+
+}  // namespace cg

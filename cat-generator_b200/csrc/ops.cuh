@@ -1,0 +1,77 @@
+// ops.cuh -- internal launchers.  All pointers are DEVICE pointers; activations are NHWC fp32
+// ([N,H,W,C], "BHWD" in stn terms) unless a name says nchw.  Everything is enqueued on cg::ctx().stream.
+#pragma once
+#include "common.cuh"
+
+namespace cg {
+
+// ---- layout (boundary <-> internal)
+int nchw_to_nhwc(const float* x, float* y, int N, int C, int HW);
+int nhwc_to_nchw(const float* x, float* y, int N, int C, int HW);
+
+// ---- pointwise
+int prelu_fwd(const float* x, const float* w, float* y, long n);
+int prelu_bwd(const float* x, const float* gy, const float* w, float* gx, float* gw_acc, long n);
+int lrelu_fwd(const float* x, float s, float* y, long n);
+int lrelu_bwd(const float* x, const float* gy, float s, float* gx, long n);
+int sigmoid_fwd(const float* x, float* y, long n);
+int sigmoid_bwd(const float* y, const float* gy, float* gx, long n);
+int add_inplace(float* a, const float* b, long n);
+int fill(float* a, float v, long n);
+int mask_channels(const float* x, const float* mask_nc, float* y, int N, int HW, int C);
+int mask_elems(const float* x, const float* mask, float* y, long n);
+
+// ---- NHWC spatial (H, W are the INPUT dims of the forward op)
+int upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C);
+int upsample2x_bwd(const float* gy, float* gx, int N, int H, int W, int C);
+int avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C);
+int avgpool2_bwd(const float* gy, float* gx, int N, int H, int W, int C);
+int maxpool2_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C);
+int maxpool2_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, int W, int C);
+
+// ---- batch norm over rows of [M, C]
+int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                 float* run_mean, float* run_var, long M, int C, float eps, float mom);
+int bn_fwd_eval(const float* x, const float* gamma, const float* beta, float* y, const float* run_mean,
+                const float* run_var, long M, int C, float eps);
+int bn_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* invstd,
+           float* gx, float* ggamma_acc, float* gbeta_acc, long M, int C);
+int colsum_acc(const float* x, float* out_acc, long M, int C);   // out[c] += sum_rows x[r,c]
+
+// ---- spatial transformer
+int affine_matrix_fwd(const float* theta, float* A, int B, int rot, int scl, int trn);
+int affine_matrix_bwd(const float* theta, const float* gA, float* gtheta, int B, int rot, int scl, int trn);
+int affine_grid_fwd(const float* A, float* grid, int B, int H, int W);
+int affine_grid_bwd(const float* ggrid, float* gA, int B, int H, int W);
+int bilinear_fwd(const float* img, const float* grid, float* out, int B, int H, int W, int C);
+int bilinear_bwd(const float* img, const float* grid, const float* gout, float* gimg, float* ggrid, int B, int H, int W, int C);
+
+// ---- criterion / optimiser / rng
+int bce(const float* p, const float* t, int n, float* loss_dev, float* g);
+// g += sign(p)*l1sign + p*l2; clamp; *loss_add_dev = l1*|p|_1 + l2*|p|^2/2 (if non-null)
+int penalty_clamp(float* g, const float* p, long n, float l1, float l1sign, float l2, float clampv, float* loss_add_dev);
+int adam(float* x, const float* g, float* m, float* v, long n, int t, float lr, float b1, float b2, float eps);
+int uniform(float* dst, long n, float lo, float hi, uint64_t seed, uint64_t offset);
+// dst[i] = (u >= p_drop) ? keep_value : 0
+int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, uint64_t offset);
+int scale_inplace(float* a, float s, long n);
+
+// ---- parameter packing (Torch layout <-> kernel layout); see conv_ref.cu
+struct ConvSpec {     // also describes nn.Linear as a 1x1 conv on a [N,1,1,in] tensor
+  int Ci, Co, k;
+  // Linear only: the Torch in/out feature index f = c*HW + s is permuted to the NHWC index s*C + c
+  int in_hw = 1, out_hw = 1;
+};
+int pack_fprop(const float* W, float* Wp, const ConvSpec& s);    // Wp[(ky,kx,ci)][co]
+int pack_dgrad(const float* W, float* Wd, const ConvSpec& s);    // Wd[(ky,kx,co)][ci], taps flipped
+int pack_bias(const float* b, float* bp, const ConvSpec& s);     // permuted for Linear with out_hw > 1
+int unpack_wgrad_acc(const float* gWp, float* gW_acc, const ConvSpec& s);   // gW (Torch layout) += gWp
+int unpack_bias_acc(const float* gbp, float* gb_acc, const ConvSpec& s);
+
+// ---- convolution engines (NHWC, stride 1, pad (k-1)/2).  bias may be null.
+int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
+int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k);
+// gWp_out[(ky,kx,ci)][co] = sum_pixels x[p+tap,ci]*gy[p,co]  (overwritten, packed layout)
+int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+
+}  // namespace cg

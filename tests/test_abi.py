@@ -1,0 +1,53 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/catgen.h
+declares, and refuses to run without a CUDA device (no CPU fallback).  No compute is called here."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+from catgen import lib
+
+
+def test_library_is_built_and_loads():
+    assert os.path.exists(lib.SO_PATH), "build with `make -C cat-generator_b200`"
+    L = lib.load()
+    assert L.cg_version().decode().startswith("catgen-b200")
+
+
+def test_every_declared_symbol_is_exported():
+    L = lib.load()
+    names = lib.declared_symbols()
+    assert len(names) > 60, names
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, "declared in include/catgen.h but not exported: %s" % missing
+
+
+def test_header_is_plain_c():
+    # the boundary must be consumable by a C compiler / LuaJIT ffi.cdef: no C++, no torch types
+    src = "#include \"catgen.h\"\nint main(void){ cg_step_cfg c; (void)c; return (int)sizeof(cg_model*) == 0; }\n"
+    inc = os.path.dirname(lib.HEADER)
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-x", "c", "-", "-fsyntax-only"],
+                       input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    # signatures only (comments stripped -- they cite reference identifiers such as cutorch.setDevice on purpose)
+    import re
+    code = re.sub(r"/\*.*?\*/", "", open(lib.HEADER).read(), flags=re.S)
+    for banned in ("torch", "at::", "Tensor", "std::", "class ", "template", "&"):
+        assert banned not in code, "non-C / torch construct %r in the C-ABI declarations" % banned
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="this check is for the GPU-less build container")
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    code = ("import sys; sys.path.insert(0, %r); from catgen import lib\n"
+            "try:\n    lib.init(0)\nexcept lib.CatgenError as e:\n    print('RAISED', e); sys.exit(0)\nsys.exit(3)\n"
+            % os.path.dirname(lib.PKG_DIR + "/"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "RAISED" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stdout or "no CUDA device" in r.stdout
+    # and a compute entry point before init refuses too
+    L = lib.load()
+    m = ctypes.c_void_p()
+    assert L.cg_model_create(ctypes.byref(m), 1, 3, 100, 1) != 0
+    assert b"cg_init" in L.cg_last_error()

@@ -22,6 +22,11 @@ static void* grow(void** p, size_t* cap, size_t bytes) {
   *cap = want;
   return *p;
 }
+void prof_begin(const char* name) {
+  Ctx::ProfRec r; r.name = name; r.flops = ctx().next_flops; r.bytes = ctx().next_bytes;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, ctx().stream); ctx().prof.push_back(r);
+}
+void prof_end() { cudaEventRecord(ctx().prof.back().b, ctx().stream); }
 void* workspace(size_t bytes) { return grow(&ctx().ws, &ctx().ws_bytes, bytes); }
 void* workspace2(size_t bytes) { return grow(&ctx().ws2, &ctx().ws2_bytes, bytes); }
 void* pinned(size_t bytes) {
@@ -99,6 +104,39 @@ const char* cg_version(void) { return "catgen-b200 0.1 (sm_100a)"; }
 int cg_sync(void) { CG_REQUIRE_INIT(); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
 int64_t cg_launch_count(void) { return ctx().launches; }
 void cg_reset_launch_count(void) { ctx().launches = 0; }
+// ---- instrumentation: replaces the reference's sys.clock() epoch timing (adversarial.lua:34,278-280)
+int cg_timer_start(void) {
+  CG_REQUIRE_INIT(); Ctx& c = ctx();
+  if (!c.t0) { CG_CUDA(cudaEventCreate(&c.t0)); CG_CUDA(cudaEventCreate(&c.t1)); }
+  CG_CUDA(cudaEventRecord(c.t0, c.stream)); return CG_OK;
+}
+int cg_timer_stop(float* ms) {
+  CG_REQUIRE_INIT(); CG_ARG(ms); Ctx& c = ctx();
+  if (!c.t0) return set_err(CG_ERR_STATE, "cg_timer_start was not called");
+  CG_CUDA(cudaEventRecord(c.t1, c.stream)); CG_CUDA(cudaEventSynchronize(c.t1)); CG_CUDA(cudaEventElapsedTime(ms, c.t0, c.t1)); return CG_OK;
+}
+int cg_profile_enable(int on) {
+  CG_REQUIRE_INIT(); Ctx& c = ctx(); cudaStreamSynchronize(c.stream);
+  for (auto& r : c.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c.prof.clear(); c.prof_on = on != 0; return CG_OK;
+}
+int cg_profile_report(char* out, int cap) {
+  CG_REQUIRE_INIT(); CG_ARG(out && cap > 64); Ctx& c = ctx();
+  CG_CUDA(cudaStreamSynchronize(c.stream));
+  struct Agg { const char* name; long n; double ms, flops, bytes; };
+  std::vector<Agg> ag;
+  for (auto& r : c.prof) {
+    float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+    size_t i = 0; for (; i < ag.size(); ++i) if (!strcmp(ag[i].name, r.name)) break;
+    if (i == ag.size()) ag.push_back({r.name, 0, 0, 0, 0});
+    ag[i].n++; ag[i].ms += ms; ag[i].flops += r.flops; ag[i].bytes += r.bytes;
+  }
+  int o = snprintf(out, cap, "[");
+  for (size_t i = 0; i < ag.size() && o < cap - 200; ++i)
+    o += snprintf(out + o, cap - o, "%s{\"kernel\":\"%s\",\"launches\":%ld,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}", i ? "," : "", ag[i].name, ag[i].n, ag[i].ms, ag[i].flops, ag[i].bytes);
+  snprintf(out + o, cap - o, "]");
+  return CG_OK;
+}
 int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
 int cg_get_conv_engine(void) { return ctx().conv_engine; }
 

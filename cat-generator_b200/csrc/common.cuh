@@ -27,7 +27,15 @@ struct Ctx {
   // data parallel
   int rank = 0, world = 1;
   void* nccl = nullptr;
+  // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
+  bool prof_on = false;
+  double next_flops = 0, next_bytes = 0;
+  struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<ProfRec> prof;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
+void prof_begin(const char* name);
+void prof_end();
 Ctx& ctx();
 
 int set_err(int code, const char* fmt, ...);
@@ -48,7 +56,10 @@ void* pinned(size_t bytes);       // pinned host staging
 // every kernel launch of this library goes through this macro so cg_launch_count() is exact
 #define CG_LAUNCH(kernel, grid, block, smem, ...)                                             \
   do {                                                                                        \
+    if (cg::ctx().prof_on) cg::prof_begin(#kernel);                                           \
     kernel<<<(grid), (block), (smem), cg::ctx().stream>>>(__VA_ARGS__);                       \
+    if (cg::ctx().prof_on) cg::prof_end();                                                    \
+    cg::ctx().next_flops = 0; cg::ctx().next_bytes = 0;                                       \
     cg::ctx().launches++;                                                                     \
     cudaError_t _e = cudaPeekAtLastError();                                                   \
     if (_e != cudaSuccess)                                                                    \

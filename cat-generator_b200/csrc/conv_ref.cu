@@ -163,6 +163,8 @@ static int conv_fwd_ref(const float* x, const float* Wp, const float* bias, floa
   bool vec = (Ci % 4 == 0) && (Co % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)Wp & 15) == 0);
   float* dst = y;
   if (S > 1) { dst = (float*)workspace(sizeof(float) * (size_t)S * M * Co); if (!dst) return CG_ERR_CUDA; }
+  double fl = 2.0 * (double)M * Co * Ktot, by = 4.0 * ((double)M * Ci + (double)Ktot * Co + (double)M * Co);
+  ctx().next_flops = fl; ctx().next_bytes = by;
   if (vec) CG_LAUNCH(k_conv_fwd<true>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
   else CG_LAUNCH(k_conv_fwd<false>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
   if (S > 1) { long n = M * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, bias, y); }
@@ -252,6 +254,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
   bool vec = (Ci % 4 == 0) && (Co % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)gy & 15) == 0);
   float* dst = gWp_out;
   if (S > 1) { dst = (float*)workspace(sizeof(float) * (size_t)S * Ktot * Co); if (!dst) return CG_ERR_CUDA; }
+  ctx().next_flops = 2.0 * (double)M * Co * Ktot; ctx().next_bytes = 4.0 * ((double)M * Ci + (double)M * Co + (double)Ktot * Co);
   if (vec) CG_LAUNCH(k_conv_wgrad<true>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
   else CG_LAUNCH(k_conv_wgrad<false>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
   if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out); }

@@ -52,6 +52,12 @@ int         cg_sync(void);                     /* cutorch.synchronize() */
 /* number of kernels of THIS library launched since the last cg_reset_launch_count (bench.py gpu_launches) */
 int64_t     cg_launch_count(void);
 void        cg_reset_launch_count(void);
+/* timing on the library's own CUDA stream (CUDA events): replaces the sys.clock() bracket of adversarial.lua:34,278-280 */
+int         cg_timer_start(void);
+int         cg_timer_stop(float* ms);
+/* per-launch event timing of every kernel + its algorithmic flops/bytes; report is a JSON array written to out */
+int         cg_profile_enable(int on);
+int         cg_profile_report(char* out, int cap);
 /* conv engine for shapes the tensor-core path supports: 0 = fp32 CUDA-core fallback only, 1 = tcgen05 (default) */
 int         cg_set_conv_engine(int engine);
 int         cg_get_conv_engine(void);

@@ -51,7 +51,7 @@ def load():
     if not os.path.exists(SO_PATH):
         raise CatgenError("%s not found: build it with `make -C %s` (or __graft_entry__.build()); "
                           "there is no CPU fallback" % (SO_PATH, PKG_DIR))
-    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(SO_PATH)
     L.cg_last_error.restype = C.c_char_p
     L.cg_version.restype = C.c_char_p
     L.cg_launch_count.restype = C.c_int64

@@ -5,6 +5,36 @@
 #include <new>
 #ifdef CG_WITH_NCCL
 #include <nccl.h>
+#include <dlfcn.h>
+// NCCL is bound at run time, not link time: a process that also imports torch already holds torch's own
+// libnccl.so.2, and a second copy pulled in by this library's DT_NEEDED broke torch's symbol resolution
+// (undefined ncclDevCommCreate, first GPU run).  Prefer the copy already loaded; otherwise load the system one.
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi a; static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return a;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+  return a;
+}
+}  // namespace
+#define CG_NCCL_API() NcclApi& N = nccl_api(); if (!N.ok) return cg::set_err(CG_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols")
 #endif
 
 namespace cg {
@@ -93,7 +123,7 @@ void cg_shutdown(void) {
   if (!c.inited) return;
   cudaStreamSynchronize(c.stream);
 #ifdef CG_WITH_NCCL
-  if (c.nccl) { ncclCommDestroy((ncclComm_t)c.nccl); c.nccl = nullptr; }
+  if (c.nccl && nccl_api().ok) { nccl_api().CommDestroy((ncclComm_t)c.nccl); c.nccl = nullptr; }
 #endif
   if (c.ws) cudaFree(c.ws); if (c.ws2) cudaFree(c.ws2); if (c.pinned) cudaFreeHost(c.pinned);
   c.ws = c.ws2 = c.pinned = nullptr; c.ws_bytes = c.ws2_bytes = c.pinned_bytes = 0;
@@ -283,8 +313,9 @@ int cg_dist_allreduce_grads(cg_model* m) {
   if (ctx().world <= 1) return CG_OK;
 #ifdef CG_WITH_NCCL
   // sum over ranks then scale by 1/world: BCE is a mean over the LOCAL batch
-  ncclResult_t r = ncclAllReduce(m->G, m->G, (size_t)m->np, ncclFloat, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
-  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", ncclGetErrorString(r));
+  CG_NCCL_API();
+  ncclResult_t r = N.AllReduce(m->G, m->G, (size_t)m->np, ncclFloat, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", N.GetErrorString(r));
   return scale_inplace(m->G, 1.f / ctx().world, m->np);
 #else
   return set_err(CG_ERR_NCCL, "library built without NCCL");
@@ -369,8 +400,9 @@ int cg_uniform_dev(float* dst, int64_t n, float lo, float hi, uint64_t seed, uin
 // ------------------------------------------------------------------ data parallel
 int cg_dist_unique_id(char id_out[128]) {
 #ifdef CG_WITH_NCCL
-  ncclUniqueId id; ncclResult_t r = ncclGetUniqueId(&id);
-  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  CG_NCCL_API();
+  ncclUniqueId id; ncclResult_t r = N.GetUniqueId(&id);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclGetUniqueId: %s", N.GetErrorString(r));
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(id_out, &id, 128); return CG_OK;
 #else
@@ -381,9 +413,10 @@ int cg_dist_init(int rank, int world, const char id[128]) {
   CG_REQUIRE_INIT(); CG_ARG(world >= 1 && rank >= 0 && rank < world);
   if (world == 1) { ctx().rank = 0; ctx().world = 1; return CG_OK; }
 #ifdef CG_WITH_NCCL
+  CG_NCCL_API();
   ncclUniqueId uid; memcpy(&uid, id, 128);
-  ncclComm_t comm; ncclResult_t r = ncclCommInitRank(&comm, world, uid, rank);
-  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+  ncclComm_t comm; ncclResult_t r = N.CommInitRank(&comm, world, uid, rank);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclCommInitRank: %s", N.GetErrorString(r));
   ctx().nccl = comm; ctx().rank = rank; ctx().world = world; return CG_OK;
 #else
   (void)id; return set_err(CG_ERR_NCCL, "library built without NCCL");

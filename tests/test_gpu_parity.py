@@ -370,7 +370,15 @@ def test_full_size_properties_c2():
     lD, lG, dout = t.step(cfg, real, rng.uniform(-1, 1, (1, B // 2, 100)).astype(np.float32), rng.uniform(-1, 1, (1, B, 100)).astype(np.float32))
     assert np.isfinite(lD).all() and np.isfinite(lG).all() and dout.shape == (B,)
     dD, dG = d.get_params() - pD0, g.get_params() - pG0
-    # first Adam step moves every parameter with a non-zero gradient by exactly lr (bias-corrected m/sqrt(v) = sign(g))
+    # First Adam step in closed form (t = 1): m = (1-b1) g, v = (1-b2) g^2, so
+    #   |dp| = lr * |g| / (|g| + eps / sqrt(1 - b2)),   eps / sqrt(1 - b2) = 3.16e-7,
+    # for EVERY element, whatever the gradient magnitude (measured on B200: G's gradients at init are ~1e-7, so
+    # most steps are well below lr -- an earlier version of this test wrongly assumed most would equal lr).
+    # After the step the library's flat gradient still holds the clamped gradient Adam consumed (G only: D's
+    # buffer also receives the G-phase accumulation, adversarial.lua:192).
     assert np.abs(dD).max() <= 1.001e-3 and np.abs(dG).max() <= 1.001e-3
-    # (elements with |g| near eps/sqrt(1-beta2) = 3e-7 move less, so only a majority is required)
-    assert np.mean(np.abs(np.abs(dG) - 1e-3) < 2e-5) > 0.5
+    gG = g.get_grads().astype(np.float64)
+    expect = -1e-3 * gG / (np.abs(gG) + 1e-8 / np.sqrt(1 - 0.999))
+    assert np.abs(gG).max() > 0
+    # parameters are O(0.1) in fp32: the update itself is only resolved to ~1e-8 absolute
+    assert np.abs(dG - expect).max() < 3e-8 + 1e-3 * 2e-3, np.abs(dG - expect).max()

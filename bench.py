@@ -111,7 +111,8 @@ def cpu_baseline(B_sample, threads, steps=1, warm=0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    from oracle import pyoracle as _po
+    cores = _po.usable_cpus()
     Bs = sample_batch(cores)
     v, dt = cpu_baseline(Bs, cores, steps=max(1, min(args.steps, 3)), warm=min(args.warmup, 1))
     sample = "G32up-c+D32_st3 RGB step at batch %d (the B=128 workload cut to %d images per step), oracle port, %d OpenMP threads" % (Bs, Bs, cores)
@@ -265,11 +266,12 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        from oracle import pyoracle as _po
+        cores = _po.usable_cpus()
         Bs = sample_batch(cores)
         v, dt = cpu_baseline(Bs, cores, steps=1, warm=0)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "one adversarial.train loop body of the same G32up-c+D32_st3 RGB workload at batch %d instead of %d (%.1f s), oracle port with %d OpenMP threads; "
+               "sample": "one adversarial.train loop body of the same G32up-c+D32_st3 RGB workload at batch %d (GPU arm: %d) taking %.1f s, oracle port with %d OpenMP threads; "
                          "Torch7/LuaJIT do not exist in this image" % (Bs, B, dt, cores)}
 
     if rank == 0:

@@ -30,6 +30,15 @@ int og_get_threads(void) {
 #endif
 }
 
+/* threads for a region with `work` independent items: never more threads than items (on a 128-core host the
+   first version forked 128 threads for 8 samples and every one of them allocated full-size scratch) */
+static int team(long work) {
+  int t = og_get_threads();
+  if (work < 1) work = 1;
+  return (long)t < work ? t : (int)work;
+}
+#define OG_SMALL 32768   /* pointwise loops shorter than this run serially */
+
 /* ------------------------------------------------------------------ GEMM helpers (serial) */
 /* C[M,N] += A[M,K] * B[K,N]  (row major) */
 static void gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {
@@ -143,7 +152,7 @@ static void col2im_add(const float* col, float* x, int Ci, int H, int W, int k) 
 void og_conv2d_fwd(const float* x, const float* W, const float* b, float* y,
                    int N, int Ci, int H, int Wd, int Co, int k) {
   long HW = (long)H * Wd; int Kc = Ci * k * k;
-#pragma omp parallel
+#pragma omp parallel num_threads(team(N))
   {
     float* col = (float*)malloc(sizeof(float) * Kc * HW);
 #pragma omp for schedule(static)
@@ -163,7 +172,7 @@ void og_conv2d_fwd(const float* x, const float* W, const float* b, float* y,
 void og_conv2d_bwd_data(const float* gy, const float* W, float* gx,
                         int N, int Ci, int H, int Wd, int Co, int k) {
   long HW = (long)H * Wd; int Kc = Ci * k * k;
-#pragma omp parallel
+#pragma omp parallel num_threads(team(N))
   {
     float* col = (float*)malloc(sizeof(float) * Kc * HW);
 #pragma omp for schedule(static)
@@ -182,11 +191,23 @@ void og_conv2d_bwd_data(const float* gy, const float* W, float* gx,
 void og_conv2d_bwd_filter(const float* x, const float* gy, float* gW, float* gb,
                           int N, int Ci, int H, int Wd, int Co, int k) {
   long HW = (long)H * Wd; int Kc = Ci * k * k;
-  long nW = (long)Co * Kc;
-#pragma omp parallel
+  long nW = (long)Co * Kc, na = nW + Co;
+  /* private accumulators per thread, bounded to ~512 MB in total, allocated once and first-touched by their
+     owner; the cross-thread sum is a parallel loop over elements in fixed thread order (no critical section) */
+  int T = team(N);
+  long cap = (512L << 20) / (long)(sizeof(float) * na); if (cap < 1) cap = 1;
+  if (T > cap) T = (int)cap;
+  float* accs = (float*)malloc(sizeof(float) * na * T);
+#pragma omp parallel num_threads(T)
   {
+#ifdef _OPENMP
+    int tid = omp_get_thread_num();
+#else
+    int tid = 0;
+#endif
+    float* acc = accs + (long)tid * na;
+    memset(acc, 0, sizeof(float) * na);
     float* col = (float*)malloc(sizeof(float) * Kc * HW);
-    float* acc = (float*)calloc(nW + Co, sizeof(float));
 #pragma omp for schedule(static)
     for (int n = 0; n < N; ++n) {
       im2col(x + (long)n * Ci * HW, col, Ci, H, Wd, k);
@@ -194,18 +215,20 @@ void og_conv2d_bwd_filter(const float* x, const float* gy, float* gW, float* gb,
       /* gW[Co,Kc] += gy[Co,HW] * col^T[HW,Kc] */
       gemm_nt(Co, Kc, (int)HW, gyn, (int)HW, col, (int)HW, acc, Kc);
       for (int o = 0; o < Co; ++o) {
-        double s = 0;
-        for (long i = 0; i < HW; ++i) s += gyn[o * HW + i];
-        acc[nW + o] += (float)s;
+        double sb = 0;
+        for (long i = 0; i < HW; ++i) sb += gyn[o * HW + i];
+        acc[nW + o] += (float)sb;
       }
     }
-#pragma omp critical
-    {
-      for (long i = 0; i < nW; ++i) gW[i] += acc[i];
-      if (gb) for (int o = 0; o < Co; ++o) gb[o] += acc[nW + o];
+    free(col);
+#pragma omp for schedule(static)
+    for (long i = 0; i < na; ++i) {
+      float sum = 0;
+      for (int t = 0; t < T; ++t) sum += accs[(long)t * na + i];
+      if (i < nW) gW[i] += sum; else if (gb) gb[i - nW] += sum;
     }
-    free(col); free(acc);
   }
+  free(accs);
 }
 
 void og_conv_upsample_fwd(const float* x, const float* W, const float* b, float* y,
@@ -216,7 +239,7 @@ void og_conv_upsample_fwd(const float* x, const float* W, const float* b, float*
 
 /* ------------------------------------------------------------------ linear (A.2) */
 void og_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int in, int out) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(out))
   for (int j = 0; j < out; ++j) {
     const float* w = W + (long)j * in;
     for (int n = 0; n < N; ++n) {
@@ -230,7 +253,7 @@ void og_linear_fwd(const float* x, const float* W, const float* b, float* y, int
 void og_linear_bwd(const float* x, const float* gy, const float* W, float* gx, float* gW, float* gb,
                    int N, int in, int out) {
   if (gx) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(N))
     for (int n = 0; n < N; ++n) {
       float* g = gx + (long)n * in;
       memset(g, 0, sizeof(float) * in);
@@ -242,7 +265,7 @@ void og_linear_bwd(const float* x, const float* gy, const float* W, float* gx, f
     }
   }
   if (gW) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(out))
     for (int j = 0; j < out; ++j) {
       float* gw = gW + (long)j * in;
       double sb = 0;
@@ -262,7 +285,7 @@ void og_bn_fwd_train(const float* x, const float* gamma, const float* beta, floa
                      float* save_mean, float* save_invstd, float* run_mean, float* run_var,
                      int N, int C, int HW, float eps, float momentum) {
   double m = (double)N * HW;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(C))
   for (int c = 0; c < C; ++c) {
     double s = 0;
     for (int n = 0; n < N; ++n) {
@@ -290,7 +313,7 @@ void og_bn_fwd_train(const float* x, const float* gamma, const float* beta, floa
 }
 void og_bn_fwd_eval(const float* x, const float* gamma, const float* beta, float* y,
                     const float* run_mean, const float* run_var, int N, int C, int HW, float eps) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(C))
   for (int c = 0; c < C; ++c) {
     float invstd = 1.f / sqrtf(run_var[c] + eps);
     for (int n = 0; n < N; ++n) {
@@ -304,7 +327,7 @@ void og_bn_bwd_train(const float* x, const float* gy, const float* gamma,
                      const float* save_mean, const float* save_invstd,
                      float* gx, float* ggamma, float* gbeta, int N, int C, int HW) {
   double m = (double)N * HW;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(C))
   for (int c = 0; c < C; ++c) {
     double sg = 0, sgx = 0;
     float mean = save_mean[c], invstd = save_invstd[c];
@@ -329,12 +352,12 @@ void og_bn_bwd_train(const float* x, const float* gy, const float* gamma,
 
 /* ------------------------------------------------------------------ pointwise */
 void og_prelu_fwd(const float* x, float w, float* y, long n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) y[i] = x[i] > 0 ? x[i] : w * x[i];
 }
 void og_prelu_bwd(const float* x, const float* gy, float w, float* gx, float* gw, long n) {
   double s = 0;
-#pragma omp parallel for schedule(static) reduction(+ : s)
+#pragma omp parallel for schedule(static) reduction(+ : s) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) {
     if (x[i] > 0) { if (gx) gx[i] = gy[i]; }
     else { if (gx) gx[i] = w * gy[i]; s += (double)x[i] * gy[i]; }
@@ -343,7 +366,7 @@ void og_prelu_bwd(const float* x, const float* gy, float w, float* gx, float* gw
 }
 void og_leakyrelu_fwd(const float* x, float s, float* y, long n) {
   /* LeakyReLU.lua:13-19: (|x|+x)/2 + (|x|-x)*(-0.5*s) */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) {
     float a = fabsf(x[i]);
     y[i] = (a + x[i]) * 0.5f + (a - x[i]) * (-0.5f * s);
@@ -351,26 +374,26 @@ void og_leakyrelu_fwd(const float* x, float s, float* y, long n) {
 }
 void og_leakyrelu_bwd(const float* x, const float* gy, float s, float* gx, long n) {
   /* LeakyReLU.lua:21-31: negative buffer = (|x|-x)*(-0.5 s) <= 0; sign()+1 is 1 where x>=0 and 0 where x<0 */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) gx[i] = x[i] >= 0 ? gy[i] : s * gy[i];
 }
 void og_sigmoid_fwd(const float* x, float* y, long n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) y[i] = 1.f / (1.f + expf(-x[i]));
 }
 void og_sigmoid_bwd(const float* y, const float* gy, float* gx, long n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) gx[i] = gy[i] * y[i] * (1.f - y[i]);
 }
 void og_upsample2x_fwd(const float* x, float* y, int NC, int H, int W) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int Y = 0; Y < 2 * H; ++Y)
       for (int X = 0; X < 2 * W; ++X)
         y[((long)c * 2 * H + Y) * 2 * W + X] = x[((long)c * H + Y / 2) * W + X / 2];
 }
 void og_upsample2x_bwd(const float* gy, float* gx, int NC, int H, int W) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int i = 0; i < H; ++i)
       for (int j = 0; j < W; ++j) {
@@ -380,7 +403,7 @@ void og_upsample2x_bwd(const float* gy, float* gx, int NC, int H, int W) {
 }
 void og_avgpool2_fwd(const float* x, float* y, int NC, int H, int W) {
   int Ho = H / 2, Wo = W / 2;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int i = 0; i < Ho; ++i)
       for (int j = 0; j < Wo; ++j) {
@@ -390,7 +413,7 @@ void og_avgpool2_fwd(const float* x, float* y, int NC, int H, int W) {
 }
 void og_avgpool2_bwd(const float* gy, float* gx, int NC, int H, int W) {
   int Ho = H / 2, Wo = W / 2;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int i = 0; i < Ho; ++i)
       for (int j = 0; j < Wo; ++j) {
@@ -401,7 +424,7 @@ void og_avgpool2_bwd(const float* gy, float* gx, int NC, int H, int W) {
 }
 void og_maxpool2_fwd(const float* x, float* y, int* idx, int NC, int H, int W) {
   int Ho = H / 2, Wo = W / 2;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int i = 0; i < Ho; ++i)
       for (int j = 0; j < Wo; ++j) {
@@ -415,7 +438,7 @@ void og_maxpool2_fwd(const float* x, float* y, int* idx, int NC, int H, int W) {
 }
 void og_maxpool2_bwd(const float* gy, const int* idx, float* gx, int NC, int H, int W) {
   int Ho = H / 2, Wo = W / 2;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c)
     for (int i = 0; i < Ho; ++i)
       for (int j = 0; j < Wo; ++j) {
@@ -426,7 +449,7 @@ void og_maxpool2_bwd(const float* gy, const int* idx, float* gx, int NC, int H, 
       }
 }
 void og_mask_channels(const float* x, const float* mask_nc, float* y, int NC, int HW) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(NC))
   for (int c = 0; c < NC; ++c) {
     float mv = mask_nc[c];
     for (int i = 0; i < HW; ++i) y[(long)c * HW + i] = x[(long)c * HW + i] * mv;
@@ -524,7 +547,7 @@ void og_affine_grid_bwd(const float* ggrid, float* gA, int B, int H, int W) {
   }
 }
 void og_bilinear_fwd(const float* img, const float* grid, float* out, int B, int H, int W, int C) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(B))
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < H; ++i)
       for (int j = 0; j < W; ++j) {
@@ -551,7 +574,7 @@ void og_bilinear_fwd(const float* img, const float* grid, float* out, int B, int
 void og_bilinear_bwd(const float* img, const float* grid, const float* gout,
                      float* gimg, float* ggrid, int B, int H, int W, int C) {
   memset(gimg, 0, sizeof(float) * (long)B * H * W * C);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(B))
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < H; ++i)
       for (int j = 0; j < W; ++j) {
@@ -583,13 +606,13 @@ void og_bilinear_bwd(const float* img, const float* grid, const float* gout,
       }
 }
 void og_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(N))
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < C; ++c)
       for (int i = 0; i < H * W; ++i) y[((long)n * H * W + i) * C + c] = x[((long)n * C + c) * H * W + i];
 }
 void og_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, int W) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team(N))
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < C; ++c)
       for (int i = 0; i < H * W; ++i) y[((long)n * C + c) * H * W + i] = x[((long)n * H * W + i) * C + c];
@@ -610,7 +633,7 @@ void og_adam_step(float* x, const float* g, float* m, float* v, long n, int t,
                   float lr, float b1, float b2, float eps) {
   double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
   float step = (float)(lr * sqrt(bc2) / bc1);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > OG_SMALL)
   for (long i = 0; i < n; ++i) {
     m[i] = b1 * m[i] + (1.f - b1) * g[i];
     v[i] = b2 * v[i] + (1.f - b2) * g[i] * g[i];

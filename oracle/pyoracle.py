@@ -36,6 +36,22 @@ def default_cfg(B, d_iters=1, g_iters=1):
     return StepCfg(B, d_iters, g_iters, 0.0, 1e-4, 0.0, 0.0, 1.0, 5.0, 1e-3, 0.9, 0.999, 1e-8)
 
 
+def usable_cpus():
+    """CPUs this process may actually use: affinity mask, further limited by a cgroup v2 CPU quota if one is set.
+    os.cpu_count() reports the machine (128 on the B200 host) and oversubscribing made the oracle crawl."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 _lib = None
 
 
@@ -45,6 +61,7 @@ def lib():
         return _lib
     if not os.path.exists(_SO):
         build()
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # idle workers sleep instead of spinning between the many short regions
     L = C.CDLL(_SO)
     i, l, f, vp = C.c_int, C.c_long, C.c_float, C.c_void_p
 
@@ -104,6 +121,7 @@ def lib():
     sig("og_train_step", None, vp, C.POINTER(StepCfg), _fp, _fp, _fp, _fp, _fp, _fp, _fp)
     sig("og_fevalD", f, vp, C.POINTER(StepCfg), _fp, _fp, _fp, _fp)
     sig("og_fevalG_on_D", f, vp, C.POINTER(StepCfg), _fp, _fp)
+    L.og_set_threads(min(usable_cpus(), 16))   # tests use batches <= 8; bench.py raises this explicitly
     _lib = L
     return L
 

@@ -205,6 +205,13 @@ void og_conv2d_bwd_filter(const float* x, const float* gy, float* gW, float* gb,
 #else
     int tid = 0;
 #endif
+    /* num_threads(T) is an upper bound: the runtime may deliver a smaller team (thread limits, cgroup quota).
+       Only slots of threads that exist are zeroed and summed. */
+#ifdef _OPENMP
+    int nt = omp_get_num_threads();
+#else
+    int nt = 1;
+#endif
     float* acc = accs + (long)tid * na;
     memset(acc, 0, sizeof(float) * na);
     float* col = (float*)malloc(sizeof(float) * Kc * HW);
@@ -224,7 +231,7 @@ void og_conv2d_bwd_filter(const float* x, const float* gy, float* gW, float* gb,
 #pragma omp for schedule(static)
     for (long i = 0; i < na; ++i) {
       float sum = 0;
-      for (int t = 0; t < T; ++t) sum += accs[(long)t * na + i];
+      for (int t = 0; t < nt; ++t) sum += accs[(long)t * na + i];
       if (i < nW) gW[i] += sum; else if (gb) gb[i - nW] += sum;
     }
   }

@@ -312,37 +312,128 @@ def test_D_masks_can_be_injected():
     assert np.abs(out[:, 0] - sig0).max() < 1e-3
 
 
-@pytest.mark.parametrize("gk,ok,Cc,B,d_it", [(lib.G32UPC, po.G32UPC, 3, 8, 1), (lib.G32UP, po.G32UP, 1, 8, 2)],
-                         ids=["c2-like", "c1c3-like"])
-def test_train_step_matches_oracle(gk, ok, Cc, B, d_it, engine):
-    """Two adversarial.train loop bodies (adversarial.lua:221-266) with replayed dropout masks: losses, D outputs
-    and post-Adam parameters against the oracle.  Adam normalises the update to ~lr=1e-3 per element, and the
-    clamp/sign structure makes single elements flip on tiny gradient differences, so parameters are compared
-    by the fraction of the step that disagrees: max |dp_gpu - dp_cpu| <= 0.5 * lr is required for 99.9% of the
-    elements and the loss/outputs carry the tight bound."""
+def _closure_inputs(rng, Cc, B):
+    real = rng.uniform(0, 1, (B // 2, Cc, 32, 32)).astype(np.float32)
+    zD = rng.uniform(-1, 1, (B // 2, 100)).astype(np.float32)
+    zG = rng.uniform(-1, 1, (B, 100)).astype(np.float32)
+    return real, zD, zG, po.make_D_masks(B, rng), po.make_D_masks(B, rng)
+
+
+def _gpu_fevalD(L, g, d, cfg, real, zD, maskD, B):
+    """adversarial.lua:221-238 + fevalD (:72-112) driven through the per-module C-ABI calls, as the Lua shim would."""
+    fake = g.forward(zD)
+    inputs = np.concatenate([real, fake]).astype(np.float32)
+    targets = np.concatenate([np.ones(B // 2, np.float32), np.zeros(B - B // 2, np.float32)])
+    d.zeroGradParameters(); d.set_masks(maskD, B, 1)
+    out = d.forward(inputs)[:, 0].copy()
+    loss = np.zeros(1, np.float32); df = np.empty(B, np.float32)
+    lib.check(L.cg_bce(P(out), P(targets), B, P(loss), P(df)))
+    d.backward(inputs, df)
+    pen = np.zeros(1, np.float32)
+    lib.check(L.cg_penalty_clamp(d.h, cfg.D_L1, cfg.D_L1, cfg.D_L2, cfg.D_clamp, P(pen)))
+    return inputs, targets, out, float(loss[0] + pen[0]), d.get_grads()
+
+
+def _gpu_fevalG(L, g, d, cfg, zG, maskG, B):
+    """fevalG_on_D (adversarial.lua:171-215) through the per-module calls."""
+    g.zeroGradParameters()
+    samples = g.forward(zG)
+    d.set_masks(maskG, B, 1)
+    out = d.forward(samples)[:, 0].copy()
+    loss = np.zeros(1, np.float32); df = np.empty(B, np.float32)
+    lib.check(L.cg_bce(P(out), P(np.ones(B, np.float32)), B, P(loss), P(df)))
+    gimg = d.backward(samples, df)
+    g.backward(zG, gimg)
+    pen = np.zeros(1, np.float32)
+    lib.check(L.cg_penalty_clamp(g.h, cfg.G_L1, cfg.G_L2, cfg.G_L2, cfg.G_clamp, P(pen)))
+    return out, float(loss[0] + pen[0]), gimg, g.get_grads()
+
+
+@pytest.mark.parametrize("gk,ok,Cc,B", [(lib.G32UPC, po.G32UPC, 3, 8), (lib.G32UP, po.G32UP, 1, 8)], ids=["c2-like", "c1c3-like"])
+def test_closures_match_oracle(gk, ok, Cc, B, engine):
+    """The two closures of adversarial.train with identical parameters, inputs and dropout masks on both sides.
+
+    What is compared is what is WELL-POSED.  Measured with the oracle alone (profiles/r01_parity_noise_floor.txt):
+    two runs of the same fp32 oracle that differ only in summation order agree on a closure's loss to 1e-7 and on
+    its gradient to 1e-8..1e-3, but after Adam updates (sign-like steps; max-pool / bilinear-cell routing in D)
+    they disagree on 0.36% of G's next steps by more than lr/2 and on the next loss by 8e-4.  So parameters are
+    re-synchronised after D's update and gradients, not trajectories, carry the parity claim.
+    Gradient bound 1e-2 of max|oracle|: the oracle itself is only 1.3e-3 from a float64 restatement on G32up-c
+    (tools/backward_precision_study.py), so nothing tighter can be claimed against it."""
+    L = lib.load()
     rng = np.random.default_rng(5)
     og, od = po.Model(ok, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
     g = models.create_G((Cc, 32, 32), 100, kind=gk); d = models.create_D((Cc, 32, 32), True)
     g.set_params(og.params); g.set_bn_running(og.bn_running); d.set_params(od.params)
-    ot = po.Trainer(og, od); t = adversarial.Trainer(g, d)
-    ocfg, cfg = po.default_cfg(B, d_it, 1), lib.default_cfg(B, d_it, 1)
-    pG0, pD0 = og.params.copy(), od.params.copy()
+    t, ot = adversarial.Trainer(g, d), po.Trainer(og, od)
+    cfg, ocfg = lib.default_cfg(B), po.default_cfg(B)
+    real, zD, zG, maskD, maskG = _closure_inputs(rng, Cc, B)
+    ltol = 1e-4 if engine == 0 else 2e-3
+    # ---- fevalD
+    inputs, targets, out, f, gD = _gpu_fevalD(L, g, d, cfg, real, zD, maskD, B)
+    fake0 = og.G_forward(zD, True)
+    assert np.abs(inputs[B // 2:] - fake0).max() < 1e-3                      # fakes fed to D (pixels, north_star bound)
+    dout0 = np.zeros(B, np.float32)
+    f0 = po.lib().og_fevalD(ot.h, C.byref(ocfg), po.P(np.concatenate([real, fake0]).astype(np.float32)), po.P(targets), po.P(maskD), po.P(dout0))
+    assert abs(f - f0) < ltol and np.abs(out - dout0).max() < max(ltol, 1e-3)
+    assert rel(gD, od.grads) < 1e-2
+    # ---- optim.adam on D on both sides, then re-synchronise (see docstring)
+    lib.check(L.cg_adam_step(t.h, 0, C.byref(cfg)))
+    po.lib().og_adam_step(po.P(od.params), po.P(od.grads), po.P(np.zeros(od.n, np.float32)), po.P(np.zeros(od.n, np.float32)), od.n, 1, 1e-3, 0.9, 0.999, 1e-8)
+    pD = d.get_params()
+    big = np.abs(od.grads) > 1e-4 * np.abs(od.grads).max()                   # away from sign-noise: both take the same step
+    assert np.mean(np.abs(pD - od.params)[big] > 0.5e-3) < 1e-3
+    d.set_params(od.params)
+    g.set_bn_running(og.bn_running)
+    # ---- fevalG_on_D
+    out, f, gimg, gG = _gpu_fevalG(L, g, d, cfg, zG, maskG, B)
+    f0 = po.lib().og_fevalG_on_D(ot.h, C.byref(ocfg), po.P(zG), po.P(maskG))
+    assert abs(f - f0) < ltol
+    assert rel(gG, og.grads) < 1e-2
+
+
+def test_fused_step_equals_unfused_sequence():
+    """cg_train_step (one C call per step) must do exactly what the per-module sequence does: GPU against GPU, same
+    kernels, so only the fp32 atomics of the bilinear scatter-add may differ."""
+    L = lib.load()
+    rng = np.random.default_rng(8)
+    Cc, B = 3, 8
+    seedp = po.Model(po.G32UPC, Cc, 100, seed=1).params.copy(); seedd = po.Model(po.D32_ST3, Cc, 100, seed=2).params.copy()
+    real, zD, zG, maskD, maskG = _closure_inputs(rng, Cc, B)
+    cfg = lib.default_cfg(B)
+    ga = models.create_G((Cc, 32, 32), 100); da = models.create_D((Cc, 32, 32), True); ga.set_params(seedp); da.set_params(seedd)
+    ta = adversarial.Trainer(ga, da)
+    da.set_masks(np.stack([maskD, maskG]), B, 2)
+    lD, lG, dout = ta.step(cfg, real[None], zD[None], zG[None])
+    gb = models.create_G((Cc, 32, 32), 100); db = models.create_D((Cc, 32, 32), True); gb.set_params(seedp); db.set_params(seedd)
+    tb = adversarial.Trainer(gb, db)
+    _, _, outb, fD, _ = _gpu_fevalD(L, gb, db, cfg, real, zD, maskD, B)
+    lib.check(L.cg_adam_step(tb.h, 0, C.byref(cfg)))
+    _, fG, _, gGb = _gpu_fevalG(L, gb, db, cfg, zG, maskG, B)
+    lib.check(L.cg_adam_step(tb.h, 1, C.byref(cfg)))
+    assert abs(lD[0] - fD) < 1e-5 and abs(lG[0] - fG) < 1e-4 and np.abs(dout - outb).max() < 1e-5
+    assert rel(ga.get_grads(), gGb) < 1e-3
+    assert np.mean(np.abs(ga.get_params() - gb.get_params()) > 0.5e-3) < 1e-3
+    assert np.abs(da.get_params() - db.get_params()).max() < 1e-5
+
+
+def test_fused_step_losses_track_oracle(engine):
+    """Two fused steps against the oracle's og_train_step: the first D update is exact-input parity (tight), what
+    follows it has passed through Adam and is compared at the measured trajectory floor (oracle vs itself: 8e-4)."""
+    rng = np.random.default_rng(5)
+    Cc, B = 3, 8
+    og, od = po.Model(po.G32UPC, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
+    g = models.create_G((Cc, 32, 32), 100); d = models.create_D((Cc, 32, 32), True)
+    g.set_params(og.params); g.set_bn_running(og.bn_running); d.set_params(od.params)
+    t, ot = adversarial.Trainer(g, d), po.Trainer(og, od)
     for step in range(2):
-        real = rng.uniform(0, 1, (d_it, B // 2, Cc, 32, 32)).astype(np.float32)
-        zD = rng.uniform(-1, 1, (d_it, B // 2, 100)).astype(np.float32)
-        zG = rng.uniform(-1, 1, (1, B, 100)).astype(np.float32)
-        masks = np.stack([po.make_D_masks(B, rng) for _ in range(d_it + 1)])
-        d.set_masks(masks, B, d_it + 1)
-        lD, lG, dout = t.step(cfg, real, zD, zG)
-        lD0, lG0, dout0 = ot.step(ocfg, real, zD, zG, masks)
-        tol = 2e-3 if engine == 0 else 1e-2
-        assert np.abs(lD - lD0).max() < tol and np.abs(lG - lG0).max() < tol
-        assert np.abs(dout - dout0).max() < tol
-    for mine, ref, p0 in ((g.get_params(), og.params, pG0), (d.get_params(), od.params, pD0)):
-        dm, dr = mine - p0, ref - p0
-        assert np.abs(dr).max() > 1e-4, "the oracle did update"
-        bad = np.mean(np.abs(dm - dr) > 0.5e-3)
-        assert bad < 1e-3, "fraction of parameters whose Adam step disagrees: %g" % bad
+        real, zD, zG, mD, mG = _closure_inputs(rng, Cc, B)
+        masks = np.stack([mD, mG]); d.set_masks(masks, B, 2)
+        lD, lG, dout = t.step(lib.default_cfg(B), real[None], zD[None], zG[None])
+        lD0, lG0, dout0 = ot.step(po.default_cfg(B), real[None], zD[None], zG[None], masks)
+        tol = (2e-4 if engine == 0 else 2e-3) if step == 0 else 5e-3
+        assert abs(lD[0] - lD0[0]) < tol and np.abs(dout - dout0).max() < max(tol, 1e-3)
+        assert abs(lG[0] - lG0[0]) < 5e-3
 
 
 # ------------------------------------------------------------------ full-size, size-independent properties

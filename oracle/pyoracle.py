@@ -143,6 +143,18 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+class _OwnedView(np.ndarray):
+    """ndarray view into memory owned by an oracle Model; keeps that Model alive (a bare view of a temporary
+    `po.Model(...).params` dangled once the temporary was collected -- found as +inf losses in a GPU test)."""
+    _owner = None
+
+
+def _view(ptr, n, owner):
+    v = np.ctypeslib.as_array(ptr, shape=(n,)).view(_OwnedView)
+    v._owner = owner
+    return v
+
+
 class Model:
     """Oracle G or D with parameters as a flat vector in nn getParameters() order."""
 
@@ -162,17 +174,17 @@ class Model:
 
     @property
     def params(self):
-        return np.ctypeslib.as_array(self.L.og_model_params(self.h), shape=(self.n,))
+        return _view(self.L.og_model_params(self.h), self.n, self)
 
     @property
     def grads(self):
-        return np.ctypeslib.as_array(self.L.og_model_grads(self.h), shape=(self.n,))
+        return _view(self.L.og_model_grads(self.h), self.n, self)
 
     @property
     def bn_running(self):
         n = C.c_long()
         p = self.L.og_model_bn_running(self.h, C.byref(n))
-        return np.ctypeslib.as_array(p, shape=(n.value,)) if n.value else np.zeros(0, np.float32)
+        return _view(p, n.value, self) if n.value else np.zeros(0, np.float32)
 
     def zero_grads(self):
         self.L.og_model_zero_grads(self.h)

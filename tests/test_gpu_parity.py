@@ -398,7 +398,9 @@ def test_fused_step_equals_unfused_sequence():
     L = lib.load()
     rng = np.random.default_rng(8)
     Cc, B = 3, 8
-    seedp = po.Model(po.G32UPC, Cc, 100, seed=1).params.copy(); seedd = po.Model(po.D32_ST3, Cc, 100, seed=2).params.copy()
+    og, od = po.Model(po.G32UPC, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
+    seedp, seedd = og.params.copy(), od.params.copy()
+    assert np.isfinite(seedp).all() and np.isfinite(seedd).all()
     real, zD, zG, maskD, maskG = _closure_inputs(rng, Cc, B)
     cfg = lib.default_cfg(B)
     ga = models.create_G((Cc, 32, 32), 100); da = models.create_D((Cc, 32, 32), True); ga.set_params(seedp); da.set_params(seedd)

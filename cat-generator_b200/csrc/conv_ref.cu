@@ -265,6 +265,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
 // conv_tc.cu provides these; they return CG_ERR_UNSUPPORTED for shapes the tensor-core path does not take.
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valued inputs (tools/backward_precision_study.py)
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   if (ctx().conv_engine == 1) { int s = conv_fwd_tc(x, Wp, bias, y, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
@@ -272,7 +273,10 @@ int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N
 }
 int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k) {
   // dgrad is a forward convolution of gy (Co channels) with the flipped/transposed weights
-  return conv_fwd(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k);
+  conv_tc_set_gradient_operands(1);
+  int s = conv_fwd(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k);
+  conv_tc_set_gradient_operands(0);
+  return s;
 }
 int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
   if (ctx().conv_engine == 1) { int s = conv_wgrad_tc(x, gy, gWp_out, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }

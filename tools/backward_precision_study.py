@@ -4,7 +4,7 @@ convolutions do to G's parameter gradient?  Off the product path; CPU only.
 Truth = float64 PyTorch restatement of G (tests/torch_ref.py) back-propagating the ACTUAL image gradient that D
 produces for the generator update (oracle fevalG_on_D path), not random noise.  Compared against it:
   fp32            : the same graph in float32 (an honest fp32 implementation)
-  tf32/fp16/bf16  : float64 arithmetic, but the operands of every conv dgrad/wgrad (gy, W, x) rounded to that format
+  tf32/fp16/bf16/fp16-scaled : float64 arithmetic, but the operands of every conv dgrad/wgrad (gy, W, x) rounded to that format
                     (models tensor-core operand rounding with fp32+ accumulation); forward kept exact
 Also reports the conditioning of the batch-norm backward: |gx| / |g_in| per BN layer.
 """
@@ -18,7 +18,14 @@ torch.set_num_threads(8)
 def rn_tf32(x):
     x32 = x.float().contiguous(); i = x32.view(torch.int32)
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
-ROUND = {"tf32": rn_tf32, "fp16": lambda x: x.half().to(x.dtype), "bf16": lambda x: x.bfloat16().to(x.dtype)}
+def fp16_scaled(x):
+    """fp16 with a per-tensor power-of-two scale putting max|x| near 2^14 (what a max-reduction + pack kernel does)."""
+    m = float(x.abs().max())
+    if m == 0: return x
+    import math
+    sc = 2.0 ** math.floor(math.log2(16384.0 / m))
+    return (x * sc).half().to(x.dtype) / sc
+ROUND = {"tf32": rn_tf32, "fp16": lambda x: x.half().to(x.dtype), "bf16": lambda x: x.bfloat16().to(x.dtype), "fp16-scaled": fp16_scaled}
 
 class ConvR(torch.autograd.Function):
     """conv2d whose BACKWARD rounds its operands (forward exact)."""
@@ -63,7 +70,7 @@ def study(kind, okind, C, B, seed=5):
     print("== %s C=%d B=%d | D out %.3f..%.3f | |gimg| max %.2e, common-mode fraction %.3f" % (
         kind, C, B, sig.min(), sig.max(), np.abs(gimg).max(), np.abs(gimg.mean(0)).max() / np.abs(gimg).max()))
     res = {}
-    for name in ("f64", "fp32", "tf32", "fp16", "bf16"):
+    for name in ("f64", "fp32", "tf32", "fp16-scaled", "fp16", "bf16"):
         dt = torch.float32 if name == "fp32" else torch.float64
         flat = torch.tensor(og.params.copy()).to(dt).requires_grad_(); zt = torch.tensor(z).to(dt)
         taps = []

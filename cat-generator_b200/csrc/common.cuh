@@ -23,6 +23,7 @@ struct Ctx {
   // scratch (grown on demand, stream-ordered reuse)
   void* ws = nullptr; size_t ws_bytes = 0;
   void* ws2 = nullptr; size_t ws2_bytes = 0;
+  void* ws3 = nullptr; size_t ws3_bytes = 0;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   // data parallel
   int rank = 0, world = 1;
@@ -40,7 +41,9 @@ Ctx& ctx();
 
 int set_err(int code, const char* fmt, ...);
 void* workspace(size_t bytes);    // device scratch #1 (split-K partials, reductions)
-void* workspace2(size_t bytes);   // device scratch #2 (boundary staging / packed operands)
+void* workspace2(size_t bytes);   // device scratch #2: boundary staging of the host-pointer entry points ONLY
+void* workspace3(size_t bytes);   // device scratch #3: tensor-core operand packing (never shared with staging: a grow
+                                  // reallocates, and ws2 pointers are live across the whole forward/backward call)
 void* pinned(size_t bytes);       // pinned host staging
 
 #define CG_CUDA(expr)                                                                         \

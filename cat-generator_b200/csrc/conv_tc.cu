@@ -17,10 +17,45 @@
 // Warp roles (160 threads): warp 4 = weight-slice producer (1 lane) ; warp 5? no -- see kernel: warps 0-3 are
 // the epilogue (they own the four TMEM lane quarters), warp 4 streams weights, warp 5 loads patches, warp 6 issues MMAs.
 #include "ops.cuh"
+#include <cuda.h>   // CUtensorMap types only; the encoder is resolved through the runtime (no -lcuda)
 
 namespace cg {
 
+// ------------------------------------------------------------------ TMA tensor maps
+// Measured (profiles/r01_launches_tc_engine.txt): fetching a patch as hundreds of 192-byte cp.async.bulk row copies
+// runs at ~66 ns per copy per SM -- the copy engine is request-rate bound -- and made every tensor-core kernel
+// 5-20x slower than its MMA time.  A patch is therefore fetched by ONE 4-D tiled TMA: box = [Wp pixels of 16 B]
+// x [Hp rows] x [planes] x [1 image] of the channel-blocked, zero-padded tensor xq[N][Cq][Hq][Wq][16 B].
+typedef CUresult (*cg_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cg_tmap_encode_fn tmap_encoder() {
+  static cg_tmap_encode_fn fn = nullptr; static bool tried = false;
+  if (!tried) {
+    tried = true; void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (cg_tmap_encode_fn)p;
+  }
+  return fn;
+}
+static int make_patch_tmap(CUtensorMap* tm, const void* xq, int ES, int N, int Cq, int Hq, int Wq, int Hp, int Wp, int planes) {
+  cg_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const int PER = 16 / ES;
+  cuuint64_t dims[4] = {(cuuint64_t)Wq * PER, (cuuint64_t)Hq, (cuuint64_t)Cq, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Wq * 16, (cuuint64_t)Hq * Wq * 16, (cuuint64_t)Cq * Hq * Wq * 16};
+  cuuint32_t box[4] = {(cuuint32_t)(Wp * PER), (cuuint32_t)Hp, (cuuint32_t)planes, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, ES == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(xq), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (dims %d x %d x %d x %d, box %d x %d x %d)", (int)r, Wq * PER, Hq, Cq, N, Wp * PER, Hp, planes);
+  return CG_OK;
+}
+
 // ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ void tma_patch_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU box.
@@ -117,7 +152,7 @@ struct TcParams {
 };
 
 template <int ES>
-__global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P) {
+__global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_constant__ CUtensorMap tmx) {
   constexpr int PER = 16 / ES, KB = 128 / ES, KSTEP = 32 / ES;   // channels per slice, K per MMA instruction
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[8], bar_wempty[8], bar_acc;
@@ -169,17 +204,13 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P) {
       }
     }
   } else if (warp == 5) {
-    // ===== patch producer: rows of the zero-padded, channel-blocked input; one bulk copy per (plane, row)
-    for (int cb = 0; cb < P.ncb; ++cb) {
-      int buf = cb & 1; uint32_t ph = (cb >> 1) & 1;
-      if (lane == 0) { mbar_wait(&bar_pempty[buf], ph ^ 1); mbar_expect_tx(&bar_pfull[buf], P.patch_bytes); }
-      __syncwarp();
-      uint8_t* dst = patch0 + (size_t)buf * P.patch_bytes;
-      const int Cq = P.Ci / PER;
-      for (int r = lane; r < planes * Hp; r += 32) {
-        int c = r / Hp, row = r % Hp;
-        const uint8_t* src = P.xq + ((((size_t)n * Cq + (size_t)cb * planes + c) * P.Hq + (y0 + row)) * P.Wq + x0) * 16;
-        bulk_g2s(dst + (size_t)c * plane_bytes + (size_t)row * Wp * 16, src, Wp * 16, &bar_pfull[buf]);
+    // ===== patch producer: ONE tiled TMA per channel block: [planes][Hp rows][Wp pixels][16 B] lands as the A-operand image
+    if (lane == 0) {
+      for (int cb = 0; cb < P.ncb; ++cb) {
+        int buf = cb & 1; uint32_t ph = (cb >> 1) & 1;
+        mbar_wait(&bar_pempty[buf], ph ^ 1);
+        mbar_expect_tx(&bar_pfull[buf], P.patch_bytes);
+        tma_patch_4d(patch0 + (size_t)buf * P.patch_bytes, &tmx, x0 * PER, y0, cb * planes, n, &bar_pfull[buf]);
       }
     }
   } else if (warp == 6) {
@@ -300,7 +331,10 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   dim3 grid(N * P.tiles_x * P.tiles_y, Co / NB);
   ctx().next_flops = 2.0 * (double)N * H * W * Co * kk * Ci;
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Co;
-  CG_LAUNCH(k_conv_tc<ES>, grid, 224, smem, P);
+  CUtensorMap tmx;
+  CG_TRY(make_patch_tmap(&tmx, xq, ES, N, Ci / PER, Hq, Wq, Hp, Wpx, CB / PER));
+  if (ES == 2) CG_LAUNCH(k_conv_tc<2>, grid, 224, smem, P, tmx);
+  else CG_LAUNCH(k_conv_tc<4>, grid, 224, smem, P, tmx);
   return CG_OK;
 }
 
@@ -366,7 +400,7 @@ struct TcWParams {
   uint32_t patch_bytes, patch_load_bytes, g_bytes;
 };
 
-__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P) {
+__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -380,7 +414,7 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P) {
   const int tap0 = tg * P.TG, kk = P.k * P.k;
   const int ntap = (tap0 + P.TG <= kk) ? P.TG : (kk - tap0);
   const long t0 = (long)P.tiles_total * z / P.Z, t1 = (long)P.tiles_total * (z + 1) / P.Z;
-  const int Cq = P.Ci / 8, Gq = P.Co / 8;
+  const int Gq = P.Co / 8;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
@@ -414,19 +448,15 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P) {
         bulk_g2s(smem + (size_t)buf * stage_bytes + P.patch_bytes, P.gq + ((size_t)t * Gq + (size_t)cob * (P.NB / 8)) * 2048, P.g_bytes, &bar_full[buf]);
       }
     }
-  } else if (warp == 5) {   // x patches: one bulk copy per (plane, row)
-    int it = 0;
-    const int planes = P.cim / 8;
-    for (long t = t0; t < t1; ++t, ++it) {
-      int buf = it & 1;
-      int tx = (int)(t % P.tiles_x); long q = t / P.tiles_x; int ty = (int)(q % P.tiles_y); long n = q / P.tiles_y;
-      if (lane == 0) { mbar_wait(&bar_empty[buf], ((it >> 1) & 1) ^ 1); mbar_expect_tx(&bar_full[buf], P.patch_load_bytes); }
-      __syncwarp();
-      uint8_t* dst = smem + (size_t)buf * stage_bytes;
-      for (int r = lane; r < planes * Hp; r += 32) {
-        int c = r / Hp, row = r % Hp;
-        const uint8_t* src = P.xq + ((((size_t)n * Cq + (size_t)cib * 16 + c) * P.Hq + (ty * 16 + row)) * P.Wq + tx * 8) * 16;
-        bulk_g2s(dst + (size_t)c * plane_bytes + (size_t)row * Wp * 16, src, Wp * 16, &bar_full[buf]);
+  } else if (warp == 5) {   // x patches: ONE tiled TMA per tile
+    if (lane == 0) {
+      int it = 0;
+      for (long t = t0; t < t1; ++t, ++it) {
+        int buf = it & 1;
+        int tx = (int)(t % P.tiles_x); long q = t / P.tiles_x; int ty = (int)(q % P.tiles_y); int n = (int)(q / P.tiles_y);
+        mbar_wait(&bar_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bar_full[buf], P.patch_load_bytes);
+        tma_patch_4d(smem + (size_t)buf * stage_bytes, &tmx, tx * 8 * 8, ty * 16, cib * 16, n, &bar_full[buf]);
       }
     }
   } else if (warp == 6) {
@@ -540,7 +570,9 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
   dim3 grid(Z, base);
   ctx().next_flops = 2.0 * (double)N * H * W * Co * kk * Ci;
   ctx().next_bytes = (double)xq_bytes + (double)gq_bytes + 4.0 * (double)kk * Ci * Co;
-  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P);
+  CUtensorMap tmx;
+  CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, P.cim / 8));
+  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx);
   long nW = (long)kk * Ci * Co;
   CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
   return CG_OK;

@@ -256,14 +256,20 @@ static int colreduce_splits(long M, int C) {
   if (want < 1) want = 1;
   return want;
 }
+// finalize kernels: one WARP per column; lane l sums partials l, l+32, ... then a fixed shuffle tree (deterministic)
+__device__ __forceinline__ void col_partials(const double* __restrict__ part, int S, int C, int c, int lane, double& s0, double& s1) {
+  s0 = 0; s1 = 0;
+  for (int s = lane; s < S; s += 32) { s0 += part[((long)s * C + c) * 2]; s1 += part[((long)s * C + c) * 2 + 1]; }
+  s0 = warp_sum_d(s0); s1 = warp_sum_d(s1);
+}
 // nn.SpatialBatchNormalization training forward (A.3): biased batch variance for normalisation,
 // unbiased into running_var, momentum 0.1
 __global__ void k_bn_stats_final(const double* __restrict__ part, int S, int C, double m, float eps, float mom,
                                  float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s0 = 0, s1 = 0;
-  for (int s = 0; s < S; ++s) { s0 += part[((long)s * C + c) * 2]; s1 += part[((long)s * C + c) * 2 + 1]; }
+  double s0, s1; col_partials(part, S, C, c, lane, s0, s1);
+  if (lane) return;
   double mu = s0 / m, var = s1 / m - mu * mu; if (var < 0) var = 0;
   mean[c] = (float)mu; invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
   if (run_mean) run_mean[c] = (1.f - mom) * run_mean[c] + mom * (float)mu;
@@ -284,7 +290,7 @@ int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y
   if (!part) return CG_ERR_CUDA;
   dim3 g(cdiv(C, 32), S), b(32, 8);
   CG_LAUNCH(k_colreduce<0>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
-  CG_LAUNCH(k_bn_stats_final, cdiv(C, 128), 128, 0, part, S, C, (double)M, eps, mom, mean, invstd, run_mean, run_var);
+  CG_LAUNCH(k_bn_stats_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, eps, mom, mean, invstd, run_mean, run_var);
   long n = M * C;
   CG_LAUNCH(k_bn_apply, grid1d(n, 256, 4), 256, 0, x, gamma, beta, mean, invstd, y, n, C);
   return CG_OK;
@@ -302,10 +308,10 @@ int bn_fwd_eval(const float* x, const float* gamma, const float* beta, float* y,
 // backward (A.3): ggamma += sum g*xhat, gbeta += sum g, gx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
 __global__ void k_bn_bwd_final(const double* __restrict__ part, int S, int C, double m, float* __restrict__ mg, float* __restrict__ mgx,
                                float* __restrict__ ggamma_acc, float* __restrict__ gbeta_acc) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s0 = 0, s1 = 0;
-  for (int s = 0; s < S; ++s) { s0 += part[((long)s * C + c) * 2]; s1 += part[((long)s * C + c) * 2 + 1]; }
+  double s0, s1; col_partials(part, S, C, c, lane, s0, s1);
+  if (lane) return;
   mg[c] = (float)(s0 / m); mgx[c] = (float)(s1 / m);
   if (gbeta_acc) gbeta_acc[c] += (float)s0;
   if (ggamma_acc) ggamma_acc[c] += (float)s1;
@@ -329,15 +335,15 @@ int bn_bwd(const float* x, const float* gy, const float* gamma, const float* mea
   double* part = (double*)wsb; float* mg = (float*)(wsb + pbytes); float* mgx = mg + C;
   dim3 g(cdiv(C, 32), S), b(32, 8);
   CG_LAUNCH(k_colreduce<1>, g, b, 0, x, gy, mean, invstd, part, M, C, rps);
-  CG_LAUNCH(k_bn_bwd_final, cdiv(C, 128), 128, 0, part, S, C, (double)M, mg, mgx, ggamma_acc, gbeta_acc);
+  CG_LAUNCH(k_bn_bwd_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, mg, mgx, ggamma_acc, gbeta_acc);
   if (gx) { long n = M * C; CG_LAUNCH(k_bn_bwd_apply, grid1d(n, 256, 4), 256, 0, x, gy, gamma, mean, invstd, mg, mgx, gx, n, C); }
   return CG_OK;
 }
 __global__ void k_colsum_final(const double* __restrict__ part, int S, int C, float* __restrict__ out_acc) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s0 = 0;
-  for (int s = 0; s < S; ++s) s0 += part[((long)s * C + c) * 2];
+  double s0, s1; col_partials(part, S, C, c, lane, s0, s1);
+  if (lane) return;
   out_acc[c] += (float)s0;
 }
 int colsum_acc(const float* x, float* out_acc, long M, int C) {
@@ -347,7 +353,7 @@ int colsum_acc(const float* x, float* out_acc, long M, int C) {
   if (!part) return CG_ERR_CUDA;
   dim3 g(cdiv(C, 32), S), b(32, 8);
   CG_LAUNCH(k_colreduce<2>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
-  CG_LAUNCH(k_colsum_final, cdiv(C, 128), 128, 0, part, S, C, out_acc);
+  CG_LAUNCH(k_colsum_final, cdiv(C, 4), 128, 0, part, S, C, out_acc);
   return CG_OK;
 }
 

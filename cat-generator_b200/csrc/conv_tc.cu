@@ -91,17 +91,30 @@ __device__ __forceinline__ void umma(uint32_t tmem, uint64_t ad, uint64_t bd, ui
 // ------------------------------------------------------------------ operand packing
 // Activations: NHWC fp32 -> channel-blocked, zero-padded xq[N][Ci/PER][Hq][Wq][PER] (PER*ES = 16 bytes),
 // Hq = roundup(H,16) + 2p, Wq = W + 2p, image at offset (p,p).  Rounding: RN to fp16 / RN to tf32.
+// Ci = real channel count of x, Cip = padded count (multiple of the slice width): channels >= Ci are zero.
 template <int ES>
-__global__ void k_pack_act(const float* __restrict__ x, uint8_t* __restrict__ xq, long nchunks, int H, int W, int Ci, int p, int Hq, int Wq) {
+__global__ void k_pack_act(const float* __restrict__ x, uint8_t* __restrict__ xq, long nchunks, int H, int W, int Ci, int Cip, int p, int Hq, int Wq) {
   constexpr int PER = 16 / ES;
-  int Cq = Ci / PER;
+  int Cq = Cip / PER;
+  const bool fast = (Ci % PER) == 0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
     int xx = (int)(i % Wq); long t = i / Wq; int yy = (int)(t % Hq); t /= Hq; int c = (int)(t % Cq); long n = t / Cq;
     int iy = yy - p, ix = xx - p;
     uint4 out = make_uint4(0, 0, 0, 0);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W && c * PER < Ci) {
       const float* s = x + ((n * H + iy) * W + ix) * Ci + c * PER;
-      if (ES == 2) {
+      if (!fast) {   // ragged channel count (1, 3): scalar gather with zero fill
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] = (c * PER + j < Ci) ? s[j] : 0.f;
+        if (ES == 2) {
+          __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+          out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
+        } else {
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(out.x) : "f"(v[0])); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(out.y) : "f"(v[1]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(out.z) : "f"(v[2])); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(out.w) : "f"(v[3]));
+        }
+      } else if (ES == 2) {
         float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
         __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
         out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -117,24 +130,25 @@ __global__ void k_pack_act(const float* __restrict__ x, uint8_t* __restrict__ xq
 // Weights: Wp[(tap,ci)][co] fp32 (conv_ref.cu layout) -> slices in main-loop order
 //   Wq[cb][tap][sub][c (KB/PER planes)][co][PER]   with KB = 128/ES channels per slice (64 fp16 / 32 tf32),
 //   cb = channel block of CB channels, sub = slice within the block.
+// Ci/Co = real sizes of Wp, Cop = padded column count of the slices; entries with ci >= Ci or co >= Co are zero.
 template <int ES>
-__global__ void k_pack_wslices(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int kk, int CB) {
+__global__ void k_pack_wslices(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int Cop, int kk, int CB) {
   constexpr int PER = 16 / ES, KB = 128 / ES, PL = KB / PER;   // PL = 8 planes per slice
   int nsub = CB / KB;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
-    int co = (int)(i % Co); long t = i / Co; int c = (int)(t % PL); t /= PL; int sub = (int)(t % nsub); t /= nsub; int tap = (int)(t % kk); int cb = (int)(t / kk);
+    int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % PL); t /= PL; int sub = (int)(t % nsub); t /= nsub; int tap = (int)(t % kk); int cb = (int)(t / kk);
     int ci0 = cb * CB + sub * KB + c * PER;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) v[j] = (co < Co && ci0 + j < Ci) ? Wp[((long)tap * Ci + ci0 + j) * Co + co] : 0.f;
     uint4 out;
     uint32_t* o = &out.x;
     if (ES == 2) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __half2 h = __floats2half2_rn(Wp[((long)tap * Ci + ci0 + 2 * j) * Co + co], Wp[((long)tap * Ci + ci0 + 2 * j + 1) * Co + co]);
-        o[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
+      for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); o[j] = *reinterpret_cast<uint32_t*>(&h); }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o[j]) : "f"(Wp[((long)tap * Ci + ci0 + j) * Co + co]));
+      for (int j = 0; j < 4; ++j) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o[j]) : "f"(v[j]));
     }
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
@@ -143,7 +157,8 @@ __global__ void k_pack_wslices(const float* __restrict__ Wp, uint8_t* __restrict
 // ------------------------------------------------------------------ the kernel
 struct TcParams {
   const uint8_t* xq; const uint8_t* wq; const float* bias; float* y;
-  int N, H, W, Ci, Co, k, p, Hq, Wq;   // Hq/Wq: padded dims of xq
+  int N, H, W, Ci, Co, k, p, Hq, Wq;   // Ci/Co: PADDED channel counts the kernel iterates over; Hq/Wq: padded dims of xq
+  int Cor;                             // real Cout = row stride of y and bound for stores / bias
   int CB, ncb;                         // channel block held in smem at once, number of blocks
   int tiles_x, tiles_y;                // tiles per image
   int NB;                              // Co columns handled by one CTA (<= 256); grid.y = Co / NB
@@ -257,7 +272,8 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
     int m = warp * 32 + lane;
     int oy = y0 + (m >> 3), ox = x0 + (m & 7);
     bool valid = oy < P.H && ox < P.W;
-    float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Co + co0;
+    float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+    const bool vec = (P.Cor & 3) == 0;
     for (int c0 = 0; c0 < P.NB; c0 += 16) {
       uint32_t v[16];
       uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                    : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;");
-      if (valid) {
+      if (valid && vec && co0 + c0 + 16 <= P.Cor) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 o;
@@ -275,6 +291,12 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
           o.z = __uint_as_float(v[j + 2]) + (P.bias ? P.bias[co0 + c0 + j + 2] : 0.f);
           o.w = __uint_as_float(v[j + 3]) + (P.bias ? P.bias[co0 + c0 + j + 3] : 0.f);
           *reinterpret_cast<float4*>(out + c0 + j) = o;
+        }
+      } else if (valid) {   // padded / ragged Cout (1, 3): only the real columns exist in y
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int co = co0 + c0 + j;
+          if (co < P.Cor) out[c0 + j] = __uint_as_float(v[j]) + (P.bias ? P.bias[co] : 0.f);
         }
       }
     }
@@ -285,14 +307,18 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
 }
 
 // ------------------------------------------------------------------ host side
+// Any channel counts are taken: Cin is zero-padded to the slice width (64 fp16 / 32 tf32 channels), Cout to 16.
+// For the 1-, 3- and 16-channel layers the padded MMA work is negligible next to the fp32 CUDA-core kernel they
+// replace (profiles/r01_launches_tc_engine.txt: 4.5 ms of a 22 ms step).
 static bool tc_shape_ok(int H, int W, int Ci, int Co, int k, int ES) {
-  int KB = 128 / ES;
-  return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && Ci % KB == 0 && Co % 16 == 0 && Co >= 16;
+  (void)Ci; (void)Co; (void)ES;
+  return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0;
 }
 
 template <int ES>
-static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
+static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k) {
   constexpr int PER = 16 / ES, KB = 128 / ES;
+  const int Ci = ((Cir + KB - 1) / KB) * KB, Co = ((Cor + 15) / 16) * 16;   // padded sizes the kernel iterates over
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p;
   const int Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
@@ -317,10 +343,10 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   if (!ws) return CG_ERR_CUDA;
   uint8_t* xq = ws; uint8_t* wq = ws + ((xq_bytes + 255) & ~(size_t)255);
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
-  CG_LAUNCH(k_pack_act<ES>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Ci, p, Hq, Wq);
-  CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wq, nw, Ci, Co, kk, CB);
+  CG_LAUNCH(k_pack_act<ES>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Cir, Ci, p, Hq, Wq);
+  CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk, CB);
   P.xq = xq; P.wq = wq; P.bias = bias; P.y = y;
-  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
+  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
   P.CB = CB; P.ncb = Ci / CB; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S;
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
   static bool attr_done[2] = {false, false};
@@ -329,8 +355,8 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
     attr_done[ES == 2 ? 0 : 1] = true;
   }
   dim3 grid(N * P.tiles_x * P.tiles_y, Co / NB);
-  ctx().next_flops = 2.0 * (double)N * H * W * Co * kk * Ci;
-  ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Co;
+  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;   // algorithmic (unpadded) work
+  ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx;
   CG_TRY(make_patch_tmap(&tmx, xq, ES, N, Ci / PER, Hq, Wq, Hp, Wpx, CB / PER));
   if (ES == 2) CG_LAUNCH(k_conv_tc<2>, grid, 224, smem, P, tmx);
@@ -374,17 +400,25 @@ __global__ void k_make_scale(const unsigned int* __restrict__ amax, float* __res
 }
 // gy NHWC fp32 -> gq[n][ty][tx][Co/8][16][8][8] fp16, scaled, rows >= H zero
 __global__ void k_pack_gtile(const float* __restrict__ gy, uint8_t* __restrict__ gq, const float* __restrict__ scale2, long nchunks,
-                             int H, int W, int Co, int tiles_x, int tiles_y) {
+                             int H, int W, int Co, int Cop, int tiles_x, int tiles_y) {
   float sc = scale2[0];
-  int Cq = Co / 8;
+  int Cq = Cop / 8;
+  const bool fast = (Co & 7) == 0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
     int px = (int)(i & 7); long t = i >> 3; int r = (int)(t & 15); t >>= 4; int c = (int)(t % Cq); t /= Cq;
     int tx = (int)(t % tiles_x); t /= tiles_x; int ty = (int)(t % tiles_y); long n = t / tiles_y;
     int y = ty * 16 + r, x = tx * 8 + px;
     uint4 out = make_uint4(0, 0, 0, 0);
-    if (y < H) {
+    if (y < H && c * 8 < Co) {
       const float* s = gy + ((n * H + y) * W + x) * Co + c * 8;
-      float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+      float4 a, b;
+      if (fast) { a = *reinterpret_cast<const float4*>(s); b = *reinterpret_cast<const float4*>(s + 4); }
+      else {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c * 8 + j < Co) ? s[j] : 0.f;
+        a = make_float4(v[0], v[1], v[2], v[3]); b = make_float4(v[4], v[5], v[6], v[7]);
+      }
       __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc), h2 = __floats2half2_rn(b.x * sc, b.y * sc), h3 = __floats2half2_rn(b.z * sc, b.w * sc);
       out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
     }
@@ -394,7 +428,8 @@ __global__ void k_pack_gtile(const float* __restrict__ gy, uint8_t* __restrict__
 
 struct TcWParams {
   const uint8_t* xq; const uint8_t* gq; float* part; const float* scale2;
-  int N, H, W, Ci, Co, k, p, Hq, Wq;
+  int N, H, W, Ci, Co, k, p, Hq, Wq;   // Ci/Co: PADDED counts (operand addressing)
+  int Cir, Cor;                        // real counts: rows per tap and row stride of the partial sums
   int tiles_x, tiles_y, tiles_total;
   int NB, TG, ntg, ncib, cim, ncob, Z;
   uint32_t patch_bytes, patch_load_bytes, g_bytes;
@@ -492,9 +527,12 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;");
     const float inv = P.scale2[1];
     const int ci_l = warp * 32 + lane;
-    const bool valid = ci_l < P.cim && t1 > t0;
+    const int ci = cib * 128 + ci_l;
+    const bool row_ok = ci_l < P.cim && ci < P.Cir;
+    const bool valid = row_ok && t1 > t0;
+    const bool vec = (P.Cor & 3) == 0;
     for (int tl = 0; tl < ntap; ++tl) {
-      float* out = P.part + ((size_t)z * kk * P.Ci + (size_t)(tap0 + tl) * P.Ci + (size_t)cib * 128 + ci_l) * P.Co + (size_t)cob * P.NB;
+      float* out = P.part + ((size_t)z * kk * P.Cir + (size_t)(tap0 + tl) * P.Cir + (size_t)ci) * P.Cor + (size_t)cob * P.NB;
       for (int c0 = 0; c0 < P.NB; c0 += 16) {
         uint32_t v[16];
         uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
@@ -503,13 +541,15 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;");
-        if (valid) {
+        const int cbase = cob * P.NB + c0;
+        if (row_ok && vec && cbase + 16 <= P.Cor) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv, __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-        } else if (ci_l < P.cim) {
+            *reinterpret_cast<float4*>(out + c0 + j) = valid ? make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv, __uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);   // empty pixel range
+        } else if (row_ok) {   // padded / ragged Cout
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);   // empty pixel range
+          for (int j = 0; j < 16; ++j) if (cbase + j < P.Cor) out[c0 + j] = valid ? __uint_as_float(v[j]) * inv : 0.f;
         }
       }
     }
@@ -527,13 +567,15 @@ __global__ void k_sum_parts(const float* __restrict__ part, int Z, long n, float
   }
 }
 
-int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
-  if (!((k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && Co % 16 == 0 && (Ci == 64 || Ci % 128 == 0))) return CG_ERR_UNSUPPORTED;
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
+  // Cin <= 64 is zero-padded to 64 (rows 64..127 of the M = 128 instruction read zero planes); Cout is padded to 16
+  if (!((k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && (Cir <= 64 || Cir % 128 == 0))) return CG_ERR_UNSUPPORTED;
+  const int Ci = Cir <= 64 ? 64 : Cir, Co = ((Cor + 15) / 16) * 16;
   if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out) & 15) != 0) return CG_ERR_UNSUPPORTED;
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
   TcWParams P{};
-  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
+  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cir = Cir; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
   P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.tiles_total = N * P.tiles_x * P.tiles_y;
   // N block: largest multiple of 16 dividing Co, <= 128, whose double-buffered stage (x patch + gy tile) fits shared memory
   const size_t patch_b = (size_t)16 * Hp * Wpx * 16;
@@ -552,28 +594,28 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
   int Z = (ctx().sm_count + base - 1) / base; if (Z > P.tiles_total / 2) Z = P.tiles_total / 2; if (Z < 1) Z = 1;
   P.Z = Z;
   size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, gq_bytes = (size_t)P.tiles_total * (Co / 8) * 2048;
-  size_t part_bytes = (size_t)Z * kk * Ci * Co * sizeof(float);
+  size_t part_bytes = (size_t)Z * kk * Cir * Cor * sizeof(float);
   size_t o1 = (xq_bytes + 255) & ~(size_t)255, o2 = o1 + ((gq_bytes + 255) & ~(size_t)255), o3 = o2 + ((part_bytes + 255) & ~(size_t)255);
   uint8_t* ws = (uint8_t*)workspace3(o3 + 256);
   if (!ws) return CG_ERR_CUDA;
   uint8_t* xq = ws; uint8_t* gq = ws + o1; float* part = (float*)(ws + o2); float* scale2 = (float*)(ws + o3); unsigned int* amax = (unsigned int*)(scale2 + 2);
   CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
-  long ng = (long)N * H * W * Co;
+  long ng = (long)N * H * W * Cor;
   CG_LAUNCH(k_absmax, grid1d(ng, 256, 8), 256, 0, gy, ng, amax);
   CG_LAUNCH(k_make_scale, 1, 1, 0, amax, scale2);
   long nx = (long)(xq_bytes / 16), ngq = (long)(gq_bytes / 16);
-  CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Ci, p, Hq, Wq);
-  CG_LAUNCH(k_pack_gtile, grid1d(ngq, 256), 256, 0, gy, gq, scale2, ngq, H, W, Co, P.tiles_x, P.tiles_y);
+  CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Cir, Ci, p, Hq, Wq);
+  CG_LAUNCH(k_pack_gtile, grid1d(ngq, 256), 256, 0, gy, gq, scale2, ngq, H, W, Cor, Co, P.tiles_x, P.tiles_y);
   P.xq = xq; P.gq = gq; P.part = part; P.scale2 = scale2;
   static bool attr_done = false;
   if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
   dim3 grid(Z, base);
-  ctx().next_flops = 2.0 * (double)N * H * W * Co * kk * Ci;
-  ctx().next_bytes = (double)xq_bytes + (double)gq_bytes + 4.0 * (double)kk * Ci * Co;
+  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;   // algorithmic (unpadded) work
+  ctx().next_bytes = (double)xq_bytes + (double)gq_bytes + 4.0 * (double)kk * Cir * Cor;
   CUtensorMap tmx;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, P.cim / 8));
   CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx);
-  long nW = (long)kk * Ci * Co;
+  long nW = (long)kk * Cir * Cor;
   CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
   return CG_OK;
 }

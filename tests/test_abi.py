@@ -51,3 +51,51 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
     m = ctypes.c_void_p()
     assert L.cg_model_create(ctypes.byref(m), 1, 3, 100, 1) != 0
     assert b"cg_init" in L.cg_last_error()
+
+
+def _protos(text):
+    """{name: (return type, [param types])} for every cg_* prototype in a C declaration text; parameter NAMES are dropped."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"--\[\[.*?\]\]", "", text, flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\s*\b(cg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        if ret.strip().startswith("typedef") or ret.strip() in ("return",):
+            continue
+        types = []
+        for a in [x.strip() for x in args.split(",")]:
+            if a in ("void", ""):
+                continue
+            arr = "*" if re.search(r"\[\d*\]\s*$", a) else ""
+            a = re.sub(r"\[\d*\]\s*$", "", a).strip()
+            m = re.match(r"^(.*?)([A-Za-z_][A-Za-z0-9_]*)$", a)          # strip the trailing identifier (the name)
+            t = (m.group(1) if m and m.group(1).strip() else a)
+            types.append(re.sub(r"\s+", "", t) + arr)
+        out[name] = (re.sub(r"\s+", "", ret), types)
+    return out
+
+
+def test_lua_cdef_matches_the_header():
+    """The Lua layer cannot be executed here (no LuaJIT), so at least its ffi.cdef must be the header's ABI verbatim."""
+    import re
+    lua = open(os.path.join(lib.PKG_DIR, "lua", "catgen_ffi.lua")).read()
+    cdef = re.search(r"ffi\.cdef\[\[(.*?)\]\]", lua, flags=re.S).group(1)
+    hdr, lu = _protos(open(lib.HEADER).read()), _protos(cdef)
+    assert len(lu) >= 25, sorted(lu)
+    for name, sig in lu.items():
+        assert name in hdr, "%s is bound in Lua but not declared in include/catgen.h" % name
+        assert sig == hdr[name], "%s: Lua %s vs header %s" % (name, sig, hdr[name])
+    # struct layout of cg_step_cfg: same field order and types
+    h_struct = re.sub(r"/\*.*?\*/", "", re.search(r"typedef struct \{(.*?)\} cg_step_cfg;", open(lib.HEADER).read(), flags=re.S).group(1), flags=re.S)
+    l_struct = re.search(r"typedef struct \{(.*?)\} cg_step_cfg;", cdef, flags=re.S).group(1)
+    def fields(t):   # "int a, b; float c;" -> [("int","a"), ("int","b"), ("float","c")]
+        out = []
+        for decl in [d.strip() for d in t.split(";") if d.strip()]:
+            ty, names = decl.split(None, 1)
+            out += [(ty, n.strip()) for n in names.split(",")]
+        return out
+    assert fields(h_struct) == fields(l_struct) and len(fields(l_struct)) == 13
+    # every Lua file says it has not been executed
+    for root, _, files in os.walk(os.path.join(lib.PKG_DIR, "lua")):
+        for f in files:
+            assert "NOT EXECUTED" in open(os.path.join(root, f)).read(), f

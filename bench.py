@@ -51,7 +51,7 @@ class Clocks:
     def __init__(self, gpu):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -59,7 +59,7 @@ class Clocks:
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.3)
         self.p.terminate(); self.p.wait()
         self.f.flush(); self.f.seek(0)
         sm, mx, reasons = [], [], set()
@@ -247,6 +247,15 @@ def main():
     h2d = 4 * (n_real + n_zd + n_zg); d2h = 4 * (B + 2)
     assert np.isfinite(outp).all(), "non-finite loss / D output in the end-to-end region"
 
+    # ---- data-parallel invariant: replicas start from the same seeds and apply the averaged gradient, so after any number
+    # of steps every rank must hold bit-identical parameters (different data per rank, one all-reduce per network per update)
+    in_sync = None
+    if dist is not None:
+        chk = torch.tensor([float(np.sum(G.get_params().astype(np.float64))), float(np.sum(D.get_params().astype(np.float64)))], dtype=torch.float64, device="cuda")
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
+
     # ---- per-kernel durations (CUDA events around every launch) on a separate short pass: events perturb the step time
     roof = None
     if rank == 0:
@@ -301,7 +310,7 @@ def main():
                "gpu_launches": launches, "wall_ms_per_step": wall_ms / K,
                "value_without_clock_sampler": world * B * K / (ms_u_max / 1e3),
                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e_max / Ke},
-               "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "last_loss": {"D": float(lossD[0]), "G": float(lossG[0])}}
+               "replicas_in_sync": in_sync, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "last_loss": {"D": float(lossD[0]), "G": float(lossG[0])}}
         print(json.dumps(out), flush=True)
     L.cg_dev_free(real_d); L.cg_dev_free(zd_d); L.cg_dev_free(zg_d)
     if dist is not None:

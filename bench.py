@@ -138,6 +138,24 @@ def main():
         return run_reference(args, rank)
     if args.warmup < 3:
         args.warmup = 3
+    import faulthandler
+    t_start = time.time()
+
+    def stage(msg):
+        """progress marker per rank on stderr; re-arms a stack dump so a hang names the exact line (multi-rank runs hung silently once)"""
+        if world > 1 or os.environ.get("CATGEN_BENCH_TRACE"):
+            sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.time() - t_start, msg)); sys.stderr.flush()
+        faulthandler.cancel_dump_traceback_later()
+        faulthandler.dump_traceback_later(45, exit=False)
+    # hard watchdog: a deadlocked collective must end as a failed run with a message, never as a hang the driver has to kill
+    limit = float(os.environ.get("CATGEN_BENCH_LIMIT_S", "900"))
+    def _watchdog():
+        time.sleep(limit)
+        sys.stderr.write("[bench rank %d] watchdog: not finished after %.0f s, aborting\n" % (rank, limit)); sys.stderr.flush()
+        faulthandler.dump_traceback(all_threads=True)
+        os._exit(3)
+    threading.Thread(target=_watchdog, daemon=True).start()
+    stage("loading libcatgen")
     from catgen import lib, models, adversarial
     L = lib.load()                       # raises if libcatgen.so is missing: there is no fallback path
     lib.init(local)
@@ -146,15 +164,19 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        stage("torch.distributed init (nccl)")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             raw = C.create_string_buffer(128)
             lib.check(L.cg_dist_unique_id(raw))
             idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+        stage("broadcast ncclUniqueId")
         dist.broadcast(idbuf, 0)
+        stage("cg_dist_init (ncclCommInitRank)")
         lib.check(L.cg_dist_init(rank, world, bytes(idbuf.cpu().numpy().tobytes())))
 
+    stage("creating models")
     B, Cc, nz = args.batch, 3, 100
     hB, img = B // 2, 3 * 1024
     G = models.create_G((Cc, 32, 32), nz, seed=1)
@@ -184,9 +206,12 @@ def main():
         lib.check(L.cg_train_step_dev(T.h, C.byref(cfg), real_d + 4 * n_real * i, zd_d + 4 * n_zd * i, zg_d + 4 * n_zg * i,
                                       lib.P(lossD) if want_loss else None, lib.P(lossG) if want_loss else None))
 
+    stage("warm-up steps")
     for i in range(W):
         dev_step(i, False)
+        stage("warm-up step %d enqueued" % i)
     barrier()
+    stage("timed region")
     clocks = Clocks(local) if rank == 0 else None
     L.cg_reset_launch_count()
     lib.check(L.cg_timer_start())
@@ -217,6 +242,7 @@ def main():
         import torch
         t = torch.tensor([ms_u.value], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_u_max = float(t.item())
 
+    stage("end-to-end region")
     # ---- end to end through the public call with HOST buffers (pinned), H2D + D2H inside the timed region
     import torch
     pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
@@ -247,6 +273,7 @@ def main():
     h2d = 4 * (n_real + n_zd + n_zg); d2h = 4 * (B + 2)
     assert np.isfinite(outp).all(), "non-finite loss / D output in the end-to-end region"
 
+    stage("replica check / profile pass")
     # ---- data-parallel invariant: replicas start from the same seeds and apply the averaged gradient, so after any number
     # of steps every rank must hold bit-identical parameters (different data per rank, one all-reduce per network per update)
     in_sync = None
@@ -312,6 +339,8 @@ def main():
                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e_max / Ke},
                "replicas_in_sync": in_sync, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "last_loss": {"D": float(lossD[0]), "G": float(lossG[0])}}
         print(json.dumps(out), flush=True)
+    stage("done")
+    faulthandler.cancel_dump_traceback_later()
     L.cg_dev_free(real_d); L.cg_dev_free(zd_d); L.cg_dev_free(zg_d)
     if dist is not None:
         dist.destroy_process_group()

@@ -285,11 +285,15 @@ def main():
 
     # ---- per-kernel durations (CUDA events around every launch) on a separate short pass: events perturb the step time
     roof = None
+    kp = min(K, 3)
     if rank == 0:
         lib.check(L.cg_profile_enable(1))
-        kp = min(K, 3)
-        for i in range(kp):
-            dev_step(W + i, False)
+    # EVERY rank runs these steps: each contains the gradient all-reduces, and a rank-0-only pass deadlocked the
+    # first 2-GPU runs (rank 0 waiting in ncclAllReduce for ranks that had already finished)
+    for i in range(kp):
+        dev_step(W + i, False)
+    barrier()
+    if rank == 0:
         buf = C.create_string_buffer(1 << 16)
         lib.check(L.cg_profile_report(buf, len(buf)))
         lib.check(L.cg_profile_enable(0))

@@ -108,7 +108,7 @@ def cpu_baseline(B_sample, threads, steps=1, warm=0):
     return B_sample / dt, dt
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out_stream):
     if rank != 0:
         return
     from oracle import pyoracle as _po
@@ -121,10 +121,20 @@ def run_reference(args, rank):
            "config": {"workload": "G32up-c + D32_st3, RGB 3x32x32, adversarial.train loop body, CPU", "batch_per_step": Bs},
            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    out_stream.write(json.dumps(out) + "\n"); out_stream.flush()
+
+
+def _quiet_stdout():
+    """C libraries print to fd 1 (NCCL's version banner landed in front of the JSON line in the first 2-GPU run).  Point fd 1 at
+    stderr for the lifetime of the process and hand back a writer on the real stdout for the single result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
+    out_stream = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -135,7 +145,7 @@ def main():
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, out_stream)
     if args.warmup < 3:
         args.warmup = 3
     import faulthandler
@@ -315,6 +325,7 @@ def main():
             roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (ach / pk["hbm_gbs"]) if ach else None,
                     "traffic": None, "peak_source": pk["source"], "share_of_step": top["ms"] / tot}
         roof["top5"] = [{"kernel": k["kernel"], "share": round(k["ms"] / tot, 4), "launches_per_step": k["launches"] / kp} for k in prof[:5]]
+        roof["kernels"] = [{"kernel": k["kernel"], "ms_per_step": round(k["ms"] / kp, 4), "launches_per_step": k["launches"] / kp} for k in prof[:30]]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -342,7 +353,7 @@ def main():
                "value_without_clock_sampler": world * B * K / (ms_u_max / 1e3),
                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e_max / Ke},
                "replicas_in_sync": in_sync, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "last_loss": {"D": float(lossD[0]), "G": float(lossG[0])}}
-        print(json.dumps(out), flush=True)
+        out_stream.write(json.dumps(out) + "\n"); out_stream.flush()
     stage("done")
     faulthandler.cancel_dump_traceback_later()
     L.cg_dev_free(real_d); L.cg_dev_free(zd_d); L.cg_dev_free(zg_d)

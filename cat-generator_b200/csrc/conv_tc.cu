@@ -162,6 +162,7 @@ struct TcParams {
   int CB, ncb;                         // channel block held in smem at once, number of blocks
   int tiles_x, tiles_y;                // tiles per image
   int NB;                              // Co columns handled by one CTA (<= 256); grid.y = Co / NB
+  int TL, ntiles;                      // tiles per CTA (1 or 2, sharing every weight slice) and total tile count
   int S;                               // weight ring depth
   uint32_t patch_bytes, slice_bytes;   // one patch buffer, one weight slice
 };
@@ -173,13 +174,16 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
   __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[8], bar_wempty[8], bar_acc;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* patch0 = smem;                              // 2 patch buffers
-  uint8_t* wring = smem + 2 * (size_t)P.patch_bytes;   // S weight slices
+  uint8_t* patch0 = smem;                                      // patch buffers [2][TL]
+  uint8_t* wring = smem + 2 * (size_t)P.TL * P.patch_bytes;    // S weight slices
 
-  // tile coordinates
-  int tile = blockIdx.x;
-  int tx = tile % P.tiles_x; tile /= P.tiles_x; int ty = tile % P.tiles_y; int n = tile / P.tiles_y;
-  const int x0 = tx * 8, y0 = ty * 16;
+  // this CTA's tiles: TL consecutive tiles share every weight slice (measured: a 128x128 tile alone needs 64 B/cycle/SM
+  // of weights from L2 and the tensor pipe sat at 23%, profiles/r01_ncu_conv3.txt)
+  const int tile0 = blockIdx.x * P.TL;
+  const int ntl = (P.ntiles - tile0) < P.TL ? (P.ntiles - tile0) : P.TL;
+  auto tile_xy = [&](int tl, int& n, int& y0, int& x0) {
+    int t = tile0 + tl; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
+  };
   const int co0 = blockIdx.y * P.NB;
   const int Hp = 16 + 2 * P.p, Wp = 8 + 2 * P.p;       // patch rows / pitch (pixels)
   const int planes = P.CB / PER;                       // 16-byte channel planes per patch buffer
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
     mbar_init(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  int ncols = 32; while (ncols < P.NB) ncols <<= 1;
+  int ncols = 32; while (ncols < P.TL * P.NB) ncols <<= 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -224,8 +228,11 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
       for (int cb = 0; cb < P.ncb; ++cb) {
         int buf = cb & 1; uint32_t ph = (cb >> 1) & 1;
         mbar_wait(&bar_pempty[buf], ph ^ 1);
-        mbar_expect_tx(&bar_pfull[buf], P.patch_bytes);
-        tma_patch_4d(patch0 + (size_t)buf * P.patch_bytes, &tmx, x0 * PER, y0, cb * planes, n, &bar_pfull[buf]);
+        mbar_expect_tx(&bar_pfull[buf], (uint32_t)ntl * P.patch_bytes);
+        for (int tl = 0; tl < ntl; ++tl) {
+          int n, y0, x0; tile_xy(tl, n, y0, x0);
+          tma_patch_4d(patch0 + (size_t)(buf * P.TL + tl) * P.patch_bytes, &tmx, x0 * PER, y0, cb * planes, n, &bar_pfull[buf]);
+        }
       }
     }
   } else if (warp == 6) {
@@ -235,12 +242,12 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)P.NB * 16, b_sbo = 128;
       const uint32_t a_lbo = plane_bytes, a_sbo = (uint32_t)Wp * 16;
-      int s = 0; uint32_t acc = 0;
+      int s = 0;
       for (int cb = 0; cb < P.ncb; ++cb) {
         int buf = cb & 1;
         mbar_wait(&bar_pfull[buf], (cb >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t pbase = smem_u32(patch0 + (size_t)buf * P.patch_bytes);
+        const uint32_t pbase0 = smem_u32(patch0 + (size_t)(buf * P.TL) * P.patch_bytes);
         for (int tap = 0; tap < kk; ++tap) {
           const uint32_t tap_off = (uint32_t)((tap / P.k) * Wp + (tap % P.k)) * 16;
           for (int sub = 0; sub < nsub; ++sub, ++s) {
@@ -248,13 +255,15 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
             mbar_wait(&bar_wfull[st], (s / P.S) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t wbase = smem_u32(wring + (size_t)st * P.slice_bytes);
+            for (int tl = 0; tl < ntl; ++tl) {        // every resident tile consumes this slice before it is released
+              const uint32_t pbase = pbase0 + (uint32_t)tl * P.patch_bytes;
 #pragma unroll
-            for (int ks = 0; ks < KB / KSTEP; ++ks) {
-              // each instruction consumes 2 consecutive 16-byte channel planes of A and of B
-              uint64_t ad = umma_desc(pbase + (uint32_t)(sub * (KB / PER) + ks * 2) * plane_bytes + tap_off, a_lbo, a_sbo);
-              uint64_t bd = umma_desc(wbase + (uint32_t)(ks * 2) * b_lbo, b_lbo, b_sbo);
-              umma<ES>(tmem, ad, bd, idesc, acc);
-              acc = 1;
+              for (int ks = 0; ks < KB / KSTEP; ++ks) {
+                // each instruction consumes 2 consecutive 16-byte channel planes of A and of B
+                uint64_t ad = umma_desc(pbase + (uint32_t)(sub * (KB / PER) + ks * 2) * plane_bytes + tap_off, a_lbo, a_sbo);
+                uint64_t bd = umma_desc(wbase + (uint32_t)(ks * 2) * b_lbo, b_lbo, b_sbo);
+                umma<ES>(tmem + (uint32_t)(tl * P.NB), ad, bd, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+              }
             }
             umma_commit(&bar_wempty[st]);             // slice may be overwritten once these MMAs retire
           }
@@ -269,14 +278,16 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
     // ===== epilogue: TMEM -> registers -> (+bias) -> NHWC fp32.  warp w owns TMEM lanes 32w..32w+31 = pixels.
     mbar_wait(&bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;");
-    int m = warp * 32 + lane;
+    const int m = warp * 32 + lane;
+    const bool vec = (P.Cor & 3) == 0;
+    for (int tl = 0; tl < ntl; ++tl) {
+    int n, y0, x0; tile_xy(tl, n, y0, x0);
     int oy = y0 + (m >> 3), ox = x0 + (m & 7);
     bool valid = oy < P.H && ox < P.W;
     float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
-    const bool vec = (P.Cor & 3) == 0;
     for (int c0 = 0; c0 < P.NB; c0 += 16) {
       uint32_t v[16];
-      uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+      uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
@@ -300,6 +311,7 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
         }
       }
     }
+    }   // tiles
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -325,18 +337,22 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   TcParams P{};
   // N columns per CTA: largest multiple of 16 that divides Co and is <= 256
   int NB = Co; while (NB > 256 || Co % NB) NB -= 16;
-  // channel block: as many 128-byte slices as keep 2 patch buffers + a >=3-deep weight ring under ~200 KB
+  // tiles per CTA and channel block: prefer TWO tiles sharing each weight slice (halves the L2->SM weight stream per MMA), then
+  // the largest channel block that keeps 2 x TL patch buffers + a >= 4-deep weight ring (>= 3 for TL = 1) inside ~212 KB
   size_t slice_bytes = (size_t)(KB / PER) * NB * 16;
-  int CB = KB;
-  for (int cand = Ci; cand >= KB; cand -= KB) {
-    if (Ci % cand) continue;
-    size_t pb = (size_t)(cand / PER) * Hp * Wpx * 16;
-    if (2 * pb + 3 * slice_bytes <= 200 * 1024) { CB = cand; break; }
-  }
+  const int ntiles = N * (W / 8) * ((H + 15) / 16);
+  int TL = 1, CB = 0;
+  for (int tl = (ntiles >= 2 && 2 * NB <= 512) ? 2 : 1; tl >= 1 && !CB; --tl)
+    for (int cand = Ci; cand >= KB; cand -= KB) {
+      if (Ci % cand) continue;
+      size_t pb = (size_t)(cand / PER) * Hp * Wpx * 16;
+      if (2 * tl * pb + (size_t)(tl == 2 ? 4 : 3) * slice_bytes <= 212 * 1024) { CB = cand; TL = tl; break; }
+    }
+  if (!CB) return CG_ERR_UNSUPPORTED;
   size_t patch_bytes = (size_t)(CB / PER) * Hp * Wpx * 16;
-  int S = (int)((212 * 1024 - 2 * patch_bytes) / slice_bytes); if (S > 8) S = 8;
+  int S = (int)((216 * 1024 - 2 * TL * patch_bytes) / slice_bytes); if (S > 8) S = 8;
   if (S < 2) return CG_ERR_UNSUPPORTED;
-  size_t smem = 2 * patch_bytes + (size_t)S * slice_bytes;
+  size_t smem = 2 * TL * patch_bytes + (size_t)S * slice_bytes;
   // operand buffers: activations then weight slices (16-byte aligned)
   size_t xq_bytes = (size_t)N * (Ci / PER) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * ES;
   uint8_t* ws = (uint8_t*)workspace3(xq_bytes + wq_bytes + 256);
@@ -347,14 +363,14 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk, CB);
   P.xq = xq; P.wq = wq; P.bias = bias; P.y = y;
   P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
-  P.CB = CB; P.ncb = Ci / CB; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S;
+  P.CB = CB; P.ncb = Ci / CB; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S; P.TL = TL; P.ntiles = ntiles;
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
   static bool attr_done[2] = {false, false};
   if (!attr_done[ES == 2 ? 0 : 1]) {
     CG_CUDA(cudaFuncSetAttribute(k_conv_tc<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done[ES == 2 ? 0 : 1] = true;
   }
-  dim3 grid(N * P.tiles_x * P.tiles_y, Co / NB);
+  dim3 grid((ntiles + TL - 1) / TL, Co / NB);
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;   // algorithmic (unpadded) work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx;

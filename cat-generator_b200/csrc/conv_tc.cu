@@ -80,6 +80,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
   // no-swizzle canonical layout, descriptor version 1; fields in 16-byte units (tools/tc_probe.cu case 1)
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+// Descriptor in two words: hi = SBO | version (constant per operand), lo = start address | LBO << 16.  Between consecutive MMAs
+// only the 14-bit start-address field moves, so the issuing thread advances `lo` with ONE add.  Measured with ncu's source page
+// (profiles/r01_ncu_conv3.txt): building both 64-bit descriptors from scratch plus runtime divisions cost 31 instructions per
+// MMA on the single issuing thread -- the kernel was issue-bound (tensor pipe 24%) while its operands were always ready.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 template <int ES>
 __device__ __forceinline__ void umma(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
   if (ES == 2)
@@ -170,6 +177,7 @@ struct TcParams {
 template <int ES>
 __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_constant__ CUtensorMap tmx) {
   constexpr int PER = 16 / ES, KB = 128 / ES, KSTEP = 32 / ES;   // channels per slice, K per MMA instruction
+  static_assert(KB / KSTEP == 4, "the issuer unrolls exactly four MMAs per weight slice");
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[8], bar_wempty[8], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -212,8 +220,8 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
     if (lane == 0) {
       // slices for all Co are stored [slice][c][Co][PER]; a CTA that owns NB < Co columns copies per plane
       const int PL = KB / PER;
-      for (int s = 0; s < nslices; ++s) {
-        int st = s % P.S; uint32_t ph = (s / P.S) & 1;
+      int st = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s, st = (st + 1 == P.S) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
         mbar_wait(&bar_wempty[st], ph ^ 1);
         mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
         uint8_t* dst = wring + (size_t)st * P.slice_bytes;
@@ -236,36 +244,41 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
       }
     }
   } else if (warp == 6) {
-    // ===== MMA issuer (one thread)
+    // ===== MMA issuer (one thread).  Everything loop-invariant is hoisted; no division, no descriptor rebuild in the loop.
     if (lane == 0) {
       const uint32_t fmt = ES == 2 ? 0u : 2u;   // F16 / TF32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t b_lbo = (uint32_t)P.NB * 16, b_sbo = 128;
-      const uint32_t a_lbo = plane_bytes, a_sbo = (uint32_t)Wp * 16;
-      int s = 0;
+      const uint32_t b_lbo = (uint32_t)P.NB * 16;
+      const uint32_t a_hi = desc_hi((uint32_t)Wp * 16), b_hi = desc_hi(128);          // SBO: patch pitch / 8 co rows
+      const uint32_t plane16 = plane_bytes >> 4, patch16 = P.patch_bytes >> 4, slice16 = P.slice_bytes >> 4;
+      const uint32_t a_kstep = 2 * plane16, b_kstep = 2 * (b_lbo >> 4), a_sub = (uint32_t)(KB / PER) * plane16;
+      const uint32_t w_lo0 = desc_lo(smem_u32(wring), b_lbo);
+      const int S = P.S, k = P.k, NB = P.NB;
+      uint32_t st = 0, wph = 0, acc0 = 0;
       for (int cb = 0; cb < P.ncb; ++cb) {
-        int buf = cb & 1;
+        const int buf = cb & 1;
         mbar_wait(&bar_pfull[buf], (cb >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t pbase0 = smem_u32(patch0 + (size_t)(buf * P.TL) * P.patch_bytes);
-        for (int tap = 0; tap < kk; ++tap) {
-          const uint32_t tap_off = (uint32_t)((tap / P.k) * Wp + (tap % P.k)) * 16;
-          for (int sub = 0; sub < nsub; ++sub, ++s) {
-            int st = s % P.S;
-            mbar_wait(&bar_wfull[st], (s / P.S) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t wbase = smem_u32(wring + (size_t)st * P.slice_bytes);
-            for (int tl = 0; tl < ntl; ++tl) {        // every resident tile consumes this slice before it is released
-              const uint32_t pbase = pbase0 + (uint32_t)tl * P.patch_bytes;
-#pragma unroll
-              for (int ks = 0; ks < KB / KSTEP; ++ks) {
-                // each instruction consumes 2 consecutive 16-byte channel planes of A and of B
-                uint64_t ad = umma_desc(pbase + (uint32_t)(sub * (KB / PER) + ks * 2) * plane_bytes + tap_off, a_lbo, a_sbo);
-                uint64_t bd = umma_desc(wbase + (uint32_t)(ks * 2) * b_lbo, b_lbo, b_sbo);
-                umma<ES>(tmem + (uint32_t)(tl * P.NB), ad, bd, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+        const uint32_t p_lo0 = desc_lo(smem_u32(patch0 + (size_t)(buf * P.TL) * P.patch_bytes), plane_bytes);
+        uint32_t row_lo = p_lo0;                                  // start of filter row ky in 16-byte units
+        for (int ky = 0; ky < k; ++ky, row_lo += (uint32_t)Wp) {
+          for (int kx = 0; kx < k; ++kx) {
+            uint32_t a_lo = row_lo + (uint32_t)kx;
+            for (int sub = 0; sub < nsub; ++sub, a_lo += a_sub) {
+              mbar_wait(&bar_wfull[st], wph);
+              asm volatile("tcgen05.fence::after_thread_sync;");
+              const uint32_t w_lo = w_lo0 + st * slice16;
+              uint32_t at = a_lo, tm = tmem;
+              for (int tl = 0; tl < ntl; ++tl, at += patch16, tm += (uint32_t)NB) {   // every resident tile consumes this slice
+                umma<ES>(tm, desc64(at, a_hi), desc64(w_lo, b_hi), idesc, acc0);
+                umma<ES>(tm, desc64(at + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+                umma<ES>(tm, desc64(at + 2 * a_kstep, a_hi), desc64(w_lo + 2 * b_kstep, b_hi), idesc, 1u);
+                umma<ES>(tm, desc64(at + 3 * a_kstep, a_hi), desc64(w_lo + 3 * b_kstep, b_hi), idesc, 1u);
               }
+              acc0 = 1u;
+              umma_commit(&bar_wempty[st]);             // slice may be overwritten once these MMAs retire
+              if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
             }
-            umma_commit(&bar_wempty[st]);             // slice may be overwritten once these MMAs retire
           }
         }
         umma_commit(&bar_pempty[buf]);
@@ -514,24 +527,29 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
     if (lane == 0) {
       // MN-major A and B (bits 15, 16), fp16, fp32 accumulate, M = 128, N = NB
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)Wp * 16, a_sbo = plane_bytes;   // k-group = next patch row; mn chunk = next ci plane
-      const uint32_t b_lbo = 128, b_sbo = 2048;                        // k-group = next 8-px row; mn chunk = next co plane
+      const uint32_t a_lbo = (uint32_t)Wp * 16;                        // k-group = next patch row; mn chunk (SBO) = next ci plane
+      const uint32_t a_hi = desc_hi(plane_bytes), b_hi = desc_hi(2048); // B: k-group (LBO) = next 8-px row (128 B); mn chunk = next co plane
+      const uint32_t a_kstep = 2 * (uint32_t)Wp, b_kstep = 16;          // two k-groups per instruction, in 16-byte units
+      const int k = P.k, NB = P.NB;
+      const int ky0 = tap0 / k, kx0 = tap0 - ky0 * k;                   // the only division: once per CTA
+      uint32_t acc0 = 0;
       int it = 0;
       for (long t = t0; t < t1; ++t, ++it) {
-        int buf = it & 1;
+        const int buf = it & 1;
         mbar_wait(&bar_full[buf], (it >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t pbase = smem_u32(smem + (size_t)buf * stage_bytes), gbase = pbase + P.patch_bytes;
-        for (int tl = 0; tl < ntap; ++tl) {
-          const int tap = tap0 + tl;
-          const uint32_t tap_off = (uint32_t)((tap / P.k) * Wp + (tap % P.k)) * 16;
+        const uint32_t pbase = smem_u32(smem + (size_t)buf * stage_bytes);
+        const uint32_t p_lo = desc_lo(pbase, a_lbo), g_lo = desc_lo(pbase + P.patch_bytes, 128);
+        int ky = ky0, kx = kx0; uint32_t tm = tmem;
+        for (int tl = 0; tl < ntap; ++tl, tm += (uint32_t)NB) {
+          const uint32_t a_lo = p_lo + (uint32_t)(ky * Wp + kx);
+          umma<2>(tm, desc64(a_lo, a_hi), desc64(g_lo, b_hi), idesc, acc0);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            uint64_t ad = umma_desc(pbase + tap_off + (uint32_t)(2 * ks) * a_lbo, a_lbo, a_sbo);
-            uint64_t bd = umma_desc(gbase + (uint32_t)(2 * ks) * b_lbo, b_lbo, b_sbo);
-            umma<2>(tmem + (uint32_t)(tl * P.NB), ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
+          for (int ks = 1; ks < 8; ++ks)
+            umma<2>(tm, desc64(a_lo + (uint32_t)ks * a_kstep, a_hi), desc64(g_lo + (uint32_t)ks * b_kstep, b_hi), idesc, 1u);
+          if (++kx == k) { kx = 0; ++ky; }
         }
+        acc0 = 1u;
         umma_commit(&bar_empty[buf]);
       }
       umma_commit(&bar_acc);

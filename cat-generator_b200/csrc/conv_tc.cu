@@ -175,7 +175,7 @@ struct TcParams {
 };
 
 template <int ES>
-__global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_constant__ CUtensorMap tmx) {
+__global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_constant__ CUtensorMap tmx) {
   constexpr int PER = 16 / ES, KB = 128 / ES, KSTEP = 32 / ES;   // channels per slice, K per MMA instruction
   static_assert(KB / KSTEP == 4, "the issuer unrolls exactly four MMAs per weight slice");
   extern __shared__ __align__(128) uint8_t smem[];
@@ -200,9 +200,12 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
   const int nslices = P.ncb * kk * nsub;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); }
-    for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
-    mbar_init(&bar_acc, 1);
+    // with two tiles per CTA there are two MMA issuers (warps 6 and 7, one tile each): a buffer is free / the accumulators are
+    // complete only when BOTH have committed
+    const uint32_t nissue = (uint32_t)P.TL;
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], nissue); }
+    for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], nissue); }
+    mbar_init(&bar_acc, nissue);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   int ncols = 32; while (ncols < P.TL * P.NB) ncols <<= 1;
@@ -243,9 +246,13 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
         }
       }
     }
-  } else if (warp == 6) {
-    // ===== MMA issuer (one thread).  Everything loop-invariant is hoisted; no division, no descriptor rebuild in the loop.
+  } else if (warp == 6 || (warp == 7 && P.TL == 2)) {
+    // ===== MMA issuers: warp 6 owns tile 0, warp 7 owns tile 1 (one thread each).  A single thread issued one fp16 MMA per ~190
+    // cycles against 64 cycles of pipe time (profiles/r01_ncu_conv3.txt); two issuers on two schedulers double the issue rate.
+    // Everything loop-invariant is hoisted; no division, no descriptor rebuild in the loop.
     if (lane == 0) {
+      const int my_tl = warp - 6;
+      const bool have_tile = my_tl < ntl;     // an odd tile count leaves the last CTA's second issuer only committing
       const uint32_t fmt = ES == 2 ? 0u : 2u;   // F16 / TF32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)P.NB * 16;
@@ -268,8 +275,8 @@ __global__ void __launch_bounds__(224, 1) k_conv_tc(TcParams P, const __grid_con
               mbar_wait(&bar_wfull[st], wph);
               asm volatile("tcgen05.fence::after_thread_sync;");
               const uint32_t w_lo = w_lo0 + st * slice16;
-              uint32_t at = a_lo, tm = tmem;
-              for (int tl = 0; tl < ntl; ++tl, at += patch16, tm += (uint32_t)NB) {   // every resident tile consumes this slice
+              if (have_tile) {
+                const uint32_t at = a_lo + (uint32_t)my_tl * patch16, tm = tmem + (uint32_t)(my_tl * NB);
                 umma<ES>(tm, desc64(at, a_hi), desc64(w_lo, b_hi), idesc, acc0);
                 umma<ES>(tm, desc64(at + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
                 umma<ES>(tm, desc64(at + 2 * a_kstep, a_hi), desc64(w_lo + 2 * b_kstep, b_hi), idesc, 1u);
@@ -388,8 +395,8 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx;
   CG_TRY(make_patch_tmap(&tmx, xq, ES, N, Ci / PER, Hq, Wq, Hp, Wpx, CB / PER));
-  if (ES == 2) CG_LAUNCH(k_conv_tc<2>, grid, 224, smem, P, tmx);
-  else CG_LAUNCH(k_conv_tc<4>, grid, 224, smem, P, tmx);
+  if (ES == 2) CG_LAUNCH(k_conv_tc<2>, grid, 256, smem, P, tmx);
+  else CG_LAUNCH(k_conv_tc<4>, grid, 256, smem, P, tmx);
   return CG_OK;
 }
 

@@ -168,6 +168,8 @@ int cg_profile_report(char* out, int cap) {
   snprintf(out + o, cap - o, "]");
   return CG_OK;
 }
+int cg_set_graph_mode(int on) { ctx().graph_mode = on ? 1 : 0; return CG_OK; }
+int cg_get_graph_mode(void) { return ctx().graph_mode; }
 int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
 int cg_get_conv_engine(void) { return ctx().conv_engine; }
 
@@ -186,7 +188,7 @@ int cg_model_free(cg_model* m) {
   if (!m) return CG_OK;
   cudaStreamSynchronize(ctx().stream);
   if (m->P) cudaFree(m->P); if (m->G) cudaFree(m->G); if (m->packed) cudaFree(m->packed); if (m->run) cudaFree(m->run);
-  if (m->masks) cudaFree(m->masks); if (m->mq) cudaFree(m->mq);
+  if (m->masks) cudaFree(m->masks); if (m->mq) cudaFree(m->mq); if (m->rng_dev) cudaFree(m->rng_dev);
   for (auto& b : m->fw) b.release(); for (auto& b : m->bw) b.release(); m->gwp.release();
   delete m; return CG_OK;
 }
@@ -292,20 +294,22 @@ int cg_trainer_create(cg_trainer** out, cg_model* G, cg_model* D) {
   CG_CUDA(cudaMalloc(&t->mG, sizeof(float) * G->np)); CG_CUDA(cudaMalloc(&t->vG, sizeof(float) * G->np));
   CG_CUDA(cudaMemsetAsync(t->mD, 0, sizeof(float) * D->np, ctx().stream)); CG_CUDA(cudaMemsetAsync(t->vD, 0, sizeof(float) * D->np, ctx().stream));
   CG_CUDA(cudaMemsetAsync(t->mG, 0, sizeof(float) * G->np, ctx().stream)); CG_CUDA(cudaMemsetAsync(t->vG, 0, sizeof(float) * G->np, ctx().stream));
+  CG_CUDA(cudaMalloc(&t->t_dev, 2 * sizeof(int))); CG_CUDA(cudaMemsetAsync(t->t_dev, 0, 2 * sizeof(int), ctx().stream));
   *out = t; return CG_OK;
 }
 int cg_trainer_free(cg_trainer* t) {
   if (!t) return CG_OK;
   cudaStreamSynchronize(ctx().stream);
-  cudaFree(t->mD); cudaFree(t->vD); cudaFree(t->mG); cudaFree(t->vG);
+  cudaFree(t->mD); cudaFree(t->vD); cudaFree(t->mG); cudaFree(t->vG); cudaFree(t->t_dev);
   t->inputs.release(); t->targets.release(); t->samples.release(); t->dout.release(); t->df.release(); t->gimg.release(); t->scal.release();
-  t->stage.release();
+  t->stage.release(); t->gin.release();
+  for (auto& e : t->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
   delete t; return CG_OK;
 }
 int cg_adam_step(cg_trainer* t, int which, const cg_step_cfg* cfg) {
   CG_REQUIRE_INIT(); CG_ARG(t && cfg && (which == 0 || which == 1));
-  if (which == 0) { t->tD += 1; CG_TRY(adam(t->D->P, t->D->G, t->mD, t->vD, t->D->np, t->tD, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->D->dirty = true; }
-  else { t->tG += 1; CG_TRY(adam(t->G->P, t->G->G, t->mG, t->vG, t->G->np, t->tG, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->G->dirty = true; }
+  if (which == 0) { CG_TRY(adam(t->D->P, t->D->G, t->mD, t->vD, t->D->np, t->t_dev + 0, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->D->dirty = true; }
+  else { CG_TRY(adam(t->G->P, t->G->G, t->mG, t->vG, t->G->np, t->t_dev + 1, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)); t->G->dirty = true; }
   return CG_OK;
 }
 
@@ -346,7 +350,7 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     CG_TRY(cg_dist_allreduce_grads(D));
     CG_TRY(penalty_clamp(D->G, D->P, D->np, c->D_L1, c->D_L1, c->D_L2, c->D_clamp, t->scal.p + si + 1));
     si += 2;
-    t->tD += 1; CG_TRY(adam(D->P, D->G, t->mD, t->vD, D->np, t->tD, c->lr, c->beta1, c->beta2, c->eps)); D->dirty = true;   // :245
+    CG_TRY(adam(D->P, D->G, t->mD, t->vD, D->np, t->t_dev + 0, c->lr, c->beta1, c->beta2, c->eps)); D->dirty = true;   // :245
   }
   for (int k = 0; k < c->g_iters; ++k) {
     // fevalG_on_D (adversarial.lua:171-215)
@@ -360,20 +364,64 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     CG_TRY(cg_dist_allreduce_grads(G));
     CG_TRY(penalty_clamp(G->G, G->P, G->np, c->G_L1, c->G_L2, c->G_L2, c->G_clamp, t->scal.p + si + 1));   // sign term uses G_L2 (adversarial.lua:206)
     si += 2;
-    t->tG += 1; CG_TRY(adam(G->P, G->G, t->mG, t->vG, G->np, t->tG, c->lr, c->beta1, c->beta2, c->eps)); G->dirty = true;   // :262
-  }
-  if (lossD || lossG) {
-    float* h = (float*)pinned(sizeof(float) * ns); if (!h) return set_err(CG_ERR_CUDA, "pinned alloc failed");
-    CG_CUDA(cudaMemcpyAsync(h, t->scal.p, sizeof(float) * ns, cudaMemcpyDeviceToHost, ctx().stream));
-    CG_CUDA(cudaStreamSynchronize(ctx().stream));
-    for (int k = 0; k < c->d_iters; ++k) if (lossD) lossD[k] = h[2 * k] + h[2 * k + 1];
-    for (int k = 0; k < c->g_iters; ++k) if (lossG) lossG[k] = h[2 * (c->d_iters + k)] + h[2 * (c->d_iters + k) + 1];
+    CG_TRY(adam(G->P, G->G, t->mG, t->vG, G->np, t->t_dev + 1, c->lr, c->beta1, c->beta2, c->eps)); G->dirty = true;   // :262
   }
   return CG_OK;
 }
+// losses of the step just enqueued: D2H + sync, kept OUTSIDE the captured graph
+static int read_losses(cg_trainer* t, const cg_step_cfg* c, float* lossD, float* lossG) {
+  if (!lossD && !lossG) return CG_OK;
+  int ns = 2 * (c->d_iters + c->g_iters);
+  float* h = (float*)pinned(sizeof(float) * ns); if (!h) return set_err(CG_ERR_CUDA, "pinned alloc failed");
+  CG_CUDA(cudaMemcpyAsync(h, t->scal.p, sizeof(float) * ns, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (int k = 0; k < c->d_iters; ++k) if (lossD) lossD[k] = h[2 * k] + h[2 * k + 1];
+  for (int k = 0; k < c->g_iters; ++k) if (lossG) lossG[k] = h[2 * (c->d_iters + k)] + h[2 * (c->d_iters + k) + 1];
+  return CG_OK;
+}
+// The step as the caller sees it: eager for the first calls of a configuration (every buffer reaches its final size, function
+// attributes are set), then captured once into a CUDA graph and replayed.  A step is ~1200 small launches and the per-launch
+// cost dominated it (profiles/r01_bench_tc_engine.json); everything a replay needs -- Adam's step count, the dropout RNG
+// offset -- lives in device memory.  Never captured: profiling runs, multi-rank runs (NCCL stays eager), forwards that consume
+// masks queued by cg_D_set_masks.  A failed capture disables graphs for that configuration and the step runs eagerly.
+static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real, const float* zD, const float* zG, float* lossD, float* lossG) {
+  Ctx& X = ctx();
+  bool eligible = X.graph_mode && !X.prof_on && X.world == 1 && !(t->D->mq && t->D->mq_next < t->D->mq_count);
+  if (!eligible) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
+  cg_trainer::StepGraph* sg = nullptr;
+  for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg))) { sg = &e; break; }
+  if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; }
+  const int B = c->B, hB = B / 2; const size_t img = (size_t)t->G->C * 1024, nz = t->G->nz;
+  const size_t nr = (size_t)c->d_iters * hB * img, nzd = (size_t)c->d_iters * hB * nz, nzg = (size_t)c->g_iters * B * nz;
+  if (sg->failed || (!sg->exec && sg->warm < 2)) {
+    sg->warm++;
+    CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG);
+  }
+  CG_TRY(t->gin.ensure(nr + nzd + nzg));
+  float* g0 = t->gin.p;
+  CG_CUDA(cudaMemcpyAsync(g0, real, sizeof(float) * nr, cudaMemcpyDeviceToDevice, X.stream));
+  CG_CUDA(cudaMemcpyAsync(g0 + nr, zD, sizeof(float) * nzd, cudaMemcpyDeviceToDevice, X.stream));
+  CG_CUDA(cudaMemcpyAsync(g0 + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyDeviceToDevice, X.stream));
+  if (!sg->exec) {
+    int64_t l0 = X.launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(X.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); sg->failed = true; }
+    else {
+      int st = train_step_core(t, c, g0, g0 + nr, g0 + nr + nzd, nullptr, nullptr);
+      cudaError_t e = cudaStreamEndCapture(X.stream, &graph);
+      if (st != CG_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&sg->exec, graph, 0) != cudaSuccess) { cudaGetLastError(); sg->exec = nullptr; sg->failed = true; }
+      if (graph) cudaGraphDestroy(graph);
+      sg->launches = X.launches - l0; X.launches = l0;      // captured, not executed yet
+    }
+    if (sg->failed) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
+  }
+  CG_CUDA(cudaGraphLaunch(sg->exec, X.stream));
+  X.launches += sg->launches;
+  return read_losses(t, c, lossD, lossG);
+}
 int cg_train_step_dev(cg_trainer* t, const cg_step_cfg* cfg, const float* real_dev, const float* zD_dev, const float* zG_dev, float* lossD, float* lossG) {
   CG_REQUIRE_INIT(); CG_ARG(t && cfg && real_dev && zD_dev && zG_dev);
-  return train_step_core(t, cfg, real_dev, zD_dev, zG_dev, lossD, lossG);
+  return train_step_run(t, cfg, real_dev, zD_dev, zG_dev, lossD, lossG);
 }
 int cg_train_step(cg_trainer* t, const cg_step_cfg* cfg, const float* real, const float* zD, const float* zG, float* lossD, float* lossG, float* d_out) {
   CG_REQUIRE_INIT(); CG_ARG(t && cfg && real && zD && zG);
@@ -386,7 +434,7 @@ int cg_train_step(cg_trainer* t, const cg_step_cfg* cfg, const float* real, cons
   CG_CUDA(cudaMemcpyAsync(s + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyHostToDevice, ctx().stream));
   float ld[16], lg[16]; CG_ARG(cfg->d_iters <= 16 && cfg->g_iters <= 16);
   // D's outputs of the last D update must be captured before the G phase overwrites dout
-  CG_TRY(train_step_core(t, cfg, s, s + nr, s + nr + nzd, ld, lg));
+  CG_TRY(train_step_run(t, cfg, s, s + nr, s + nr + nzd, ld, lg));
   if (lossD) for (int k = 0; k < cfg->d_iters; ++k) lossD[k] = ld[k];
   if (lossG) for (int k = 0; k < cfg->g_iters; ++k) lossG[k] = lg[k];
   if (d_out) { CG_CUDA(cudaMemcpyAsync(d_out, t->dout.p, sizeof(float) * B, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); }

@@ -18,6 +18,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   int conv_engine = 1;
+  int graph_mode = 1;           // replay the training step as a CUDA graph once warm (cg_set_graph_mode)
   int64_t launches = 0;
   char err[1024] = {0};
   // scratch (grown on demand, stream-ordered reuse)

@@ -146,6 +146,9 @@ int model_build(cg_model* m) {
     CG_TRY(init_layer(m, m->h1, false)); CG_TRY(set_scalar(m->hpw, quarter));
     CG_TRY(init_layer(m, m->h2, false));
   }
+  // dropout masks continue the Philox stream after the initialisation draws
+  CG_CUDA(cudaMalloc(&m->rng_dev, sizeof(unsigned long long)));
+  { unsigned long long v = m->rng_offset; CG_CUDA(cudaMemcpyAsync(m->rng_dev, &v, sizeof(v), cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); }
   m->dirty = true;
   return CG_OK;
 }
@@ -314,9 +317,11 @@ static int ensure_masks(cg_model* d, int B) {
   }
   long nsp = (long)B * (64 * 4 + 128), nh = (long)B * 320, nf = (long)B * 256;
   if (d->training) {   // nn.SpatialDropout(0.2) x5 (no rescale), SpatialDropout(0.5), nn.Dropout(0.5) v2 (x2) -- SURVEY.md A.12
-    CG_TRY(bernoulli_mask(d->masks, nsp, 0.2f, 1.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nsp + 3) / 4 + 1;
-    CG_TRY(bernoulli_mask(d->masks + nsp, nh, 0.5f, 1.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nh + 3) / 4 + 1;
-    CG_TRY(bernoulli_mask(d->masks + nsp + nh, nf, 0.5f, 2.f, d->seed, d->rng_offset)); d->rng_offset += (uint64_t)(nf + 3) / 4 + 1;
+    uint64_t r1 = (uint64_t)(nsp + 3) / 4 + 1, r2 = r1 + (uint64_t)(nh + 3) / 4 + 1, r3 = r2 + (uint64_t)(nf + 3) / 4 + 1;
+    CG_TRY(bernoulli_mask(d->masks, nsp, 0.2f, 1.f, d->seed, d->rng_dev, 0));
+    CG_TRY(bernoulli_mask(d->masks + nsp, nh, 0.5f, 1.f, d->seed, d->rng_dev, r1));
+    CG_TRY(bernoulli_mask(d->masks + nsp + nh, nf, 0.5f, 2.f, d->seed, d->rng_dev, r2));
+    CG_TRY(rng_advance(d->rng_dev, r3));
   } else {             // evaluate(): SpatialDropout scales by (1-p); Dropout v2 is the identity
     CG_TRY(fill(d->masks, 0.8f, nsp)); CG_TRY(fill(d->masks + nsp, 0.5f, nh)); CG_TRY(fill(d->masks + nsp + nh, 1.f, nf));
   }

@@ -29,7 +29,8 @@ struct cg_model {
   float* packed = nullptr; size_t packed_floats = 0;
   bool dirty = true;                        // packed operands stale w.r.t. P
   int training = 1;
-  uint64_t seed = 0, rng_offset = 0;
+  uint64_t seed = 0, rng_offset = 0;          // rng_offset: host counter used only while initialising parameters
+  unsigned long long* rng_dev = nullptr;      // Philox offset of the dropout masks, in device memory (graph replay)
   std::vector<cg::DBuf> fw, bw; int nfw = 0, nbw = 0;
   cg::DBuf gwp;                              // packed wgrad scratch
   int B = 0;
@@ -52,8 +53,12 @@ struct cg_model {
 struct cg_trainer {
   cg_model *G, *D;
   float *mD, *vD, *mG, *vG;
-  int tD = 0, tG = 0;
+  int* t_dev = nullptr;                       // [tD, tG]: optim.adam step counters, in device memory (graph replay)
   cg::DBuf inputs, targets, samples, dout, df, gimg, scal, stage;
+  // CUDA-graph replay of the step (capi.cu): fixed input buffers + one instantiated graph per step configuration
+  cg::DBuf gin;
+  struct StepGraph { cg_step_cfg cfg; int warm = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::vector<StepGraph> graphs;
 };
 
 namespace cg {

@@ -561,8 +561,19 @@ int penalty_clamp(float* g, const float* p, long n, float l1, float l1sign, floa
   return CG_OK;
 }
 // optim.adam (A.8): eps added to sqrt(v) BEFORE the bias correction is applied through stepSize
+// Step count and RNG offset live in DEVICE memory so that a captured CUDA graph of the training step replays correctly
+// (a host value passed as a kernel argument would be frozen at capture time).
+__global__ void k_inc_i32(int* p) { *p += 1; }
+__global__ void k_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
 __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                       float step, float b1, float b2, float eps) {
+                       const int* __restrict__ t_dev, float lr, float b1, float b2, float eps) {
+  __shared__ float step_s;
+  if (threadIdx.x == 0) {   // optim.adam: stepSize = lr * sqrt(1 - beta2^t) / (1 - beta1^t), t already incremented
+    int t = *t_dev;
+    step_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
+  __syncthreads();
+  const float step = step_s;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float gv = g[i];
     float mv = b1 * m[i] + (1.f - b1) * gv;
@@ -571,10 +582,10 @@ __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float
     x[i] -= step * mv / (sqrtf(vv) + eps);
   }
 }
-int adam(float* x, const float* g, float* m, float* v, long n, int t, float lr, float b1, float b2, float eps) {
-  double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
-  float step = (float)(lr * sqrt(bc2) / bc1);
-  CG_LAUNCH(k_adam, grid1d(n, 256, 4), 256, 0, x, g, m, v, n, step, b1, b2, eps); return CG_OK;
+// t_dev: device step counter of this parameter vector; it is incremented here (t <- t + 1) and then used
+int adam(float* x, const float* g, float* m, float* v, long n, int* t_dev, float lr, float b1, float b2, float eps) {
+  CG_LAUNCH(k_inc_i32, 1, 1, 0, t_dev);
+  CG_LAUNCH(k_adam, grid1d(n, 256, 4), 256, 0, x, g, m, v, n, (const int*)t_dev, lr, b1, b2, eps); return CG_OK;
 }
 __global__ void k_uniform(float* __restrict__ dst, long n, float lo, float hi, uint32_t k0, uint32_t k1, uint64_t offset) {
   long nq = (n + 3) / 4;
@@ -589,7 +600,9 @@ __global__ void k_uniform(float* __restrict__ dst, long n, float lo, float hi, u
 int uniform(float* dst, long n, float lo, float hi, uint64_t seed, uint64_t offset) {
   CG_LAUNCH(k_uniform, grid1d((n + 3) / 4, 256), 256, 0, dst, n, lo, hi, (uint32_t)seed, (uint32_t)(seed >> 32), offset); return CG_OK;
 }
-__global__ void k_bernoulli(float* __restrict__ dst, long n, float p_drop, float keep, uint32_t k0, uint32_t k1, uint64_t offset) {
+__global__ void k_bernoulli(float* __restrict__ dst, long n, float p_drop, float keep, uint32_t k0, uint32_t k1,
+                            const unsigned long long* __restrict__ offset_dev, unsigned long long rel) {
+  const uint64_t offset = *offset_dev + rel;
   long nq = (n + 3) / 4;
   for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < nq; q += (long)gridDim.x * blockDim.x) {
     uint64_t ctr = offset + (uint64_t)q;
@@ -599,8 +612,10 @@ __global__ void k_bernoulli(float* __restrict__ dst, long n, float p_drop, float
     for (int j = 0; j < 4; ++j) { long i = q * 4 + j; if (i < n) dst[i] = u01(c[j]) >= p_drop ? keep : 0.f; }
   }
 }
-int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, uint64_t offset) {
-  CG_LAUNCH(k_bernoulli, grid1d((n + 3) / 4, 256), 256, 0, dst, n, p_drop, keep_value, (uint32_t)seed, (uint32_t)(seed >> 32), offset); return CG_OK;
+// offset = *offset_dev + rel (Philox counter); the caller advances *offset_dev with rng_advance after a group of masks
+int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, const unsigned long long* offset_dev, uint64_t rel) {
+  CG_LAUNCH(k_bernoulli, grid1d((n + 3) / 4, 256), 256, 0, dst, n, p_drop, keep_value, (uint32_t)seed, (uint32_t)(seed >> 32), offset_dev, (unsigned long long)rel); return CG_OK;
 }
+int rng_advance(unsigned long long* offset_dev, uint64_t by) { CG_LAUNCH(k_add_u64, 1, 1, 0, offset_dev, (unsigned long long)by); return CG_OK; }
 
 }  // namespace cg

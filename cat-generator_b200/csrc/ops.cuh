@@ -50,10 +50,11 @@ int bilinear_bwd(const float* img, const float* grid, const float* gout, float* 
 int bce(const float* p, const float* t, int n, float* loss_dev, float* g);
 // g += sign(p)*l1sign + p*l2; clamp; *loss_add_dev = l1*|p|_1 + l2*|p|^2/2 (if non-null)
 int penalty_clamp(float* g, const float* p, long n, float l1, float l1sign, float l2, float clampv, float* loss_add_dev);
-int adam(float* x, const float* g, float* m, float* v, long n, int t, float lr, float b1, float b2, float eps);
+int adam(float* x, const float* g, float* m, float* v, long n, int* t_dev, float lr, float b1, float b2, float eps);   // increments *t_dev, then steps
 int uniform(float* dst, long n, float lo, float hi, uint64_t seed, uint64_t offset);
 // dst[i] = (u >= p_drop) ? keep_value : 0
-int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, uint64_t offset);
+int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, const unsigned long long* offset_dev, uint64_t rel);
+int rng_advance(unsigned long long* offset_dev, uint64_t by);
 int scale_inplace(float* a, float s, long n);
 
 // ---- parameter packing (Torch layout <-> kernel layout); see conv_ref.cu

@@ -58,6 +58,10 @@ int         cg_timer_stop(float* ms);
 /* per-launch event timing of every kernel + its algorithmic flops/bytes; report is a JSON array written to out */
 int         cg_profile_enable(int on);
 int         cg_profile_report(char* out, int cap);
+/* 1 (default): cg_train_step* replay the step as a CUDA graph once a configuration has run twice eagerly; 0: always eager.
+   Results are the same either way (Adam's step count and the dropout RNG offset live in device memory). */
+int         cg_set_graph_mode(int on);
+int         cg_get_graph_mode(void);
 /* conv engine for shapes the tensor-core path supports: 0 = fp32 CUDA-core fallback only, 1 = tcgen05 (default) */
 int         cg_set_conv_engine(int engine);
 int         cg_get_conv_engine(void);

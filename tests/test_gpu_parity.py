@@ -480,6 +480,40 @@ def test_fused_step_equals_unfused_sequence():
     assert np.abs(da.get_params() - db.get_params()).max() < 1e-5
 
 
+def test_graph_replay_matches_eager():
+    """cg_train_step replays the step as a CUDA graph from the third call of a configuration on.  Same initial state, same
+    inputs, graphs off vs on: the first replayed step (call 3) must reproduce the eager loss and D outputs; afterwards only the
+    bilinear scatter's atomic order differs and the trajectories may drift at the floor measured for the oracle itself (8e-4 on
+    the loss).  Adam's step count and the dropout RNG offset are device-side, so replay advances both (losses keep changing)."""
+    L = lib.load()
+    Cc, B = 3, 8
+    rng = np.random.default_rng(11)
+    steps = [(_closure_inputs(rng, Cc, B)) for _ in range(6)]
+    out = {}
+    try:
+        for mode in (0, 1):
+            lib.check(L.cg_set_graph_mode(mode))
+            g = models.create_G((Cc, 32, 32), 100, seed=1); d = models.create_D((Cc, 32, 32), True, seed=2)
+            t = adversarial.Trainer(g, d)
+            L.cg_reset_launch_count()
+            rec = []
+            for real, zD, zG, _, _ in steps:
+                n0 = L.cg_launch_count()
+                lD, lG, dout = t.step(lib.default_cfg(B), real[None], zD[None], zG[None])
+                rec.append((float(lD[0]), float(lG[0]), dout.copy(), L.cg_launch_count() - n0))
+            out[mode] = (rec, g.get_params(), d.get_params())
+    finally:
+        lib.check(L.cg_set_graph_mode(1))
+    e, r = out[0][0], out[1][0]
+    for i in range(6):
+        tol = 1e-4 if i < 3 else 5e-3
+        assert abs(e[i][0] - r[i][0]) < tol and abs(e[i][1] - r[i][1]) < tol, (i, e[i][:2], r[i][:2])
+        assert np.abs(e[i][2] - r[i][2]).max() < max(tol, 1e-3)
+        assert r[i][3] == e[i][3] > 500, "replay accounts for the same number of kernel launches as the eager step"
+    assert len({round(x[0], 6) for x in r}) == 6, "every replay sees new dropout masks and a new Adam step (losses differ)"
+    assert np.mean(np.abs(out[0][1] - out[1][1]) > 0.5e-3) < 2e-2 and np.mean(np.abs(out[0][2] - out[1][2]) > 0.5e-3) < 2e-2
+
+
 def test_fused_step_losses_track_oracle(engine):
     """Two fused steps against the oracle's og_train_step: the first D update is exact-input parity (tight), what
     follows it has passed through Adam and is compared at the measured trajectory floor (oracle vs itself: 8e-4)."""

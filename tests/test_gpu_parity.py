@@ -506,9 +506,12 @@ def test_graph_replay_matches_eager():
         lib.check(L.cg_set_graph_mode(1))
     e, r = out[0][0], out[1][0]
     for i in range(6):
-        tol = 1e-4 if i < 3 else 5e-3
-        assert abs(e[i][0] - r[i][0]) < tol and abs(e[i][1] - r[i][1]) < tol, (i, e[i][:2], r[i][:2])
-        assert np.abs(e[i][2] - r[i][2]).max() < max(tol, 1e-3)
+        # lossD and D's outputs are computed BEFORE any update inside the step: tight through the first replay (call 3).
+        # lossG is computed after D's Adam update in the same step, i.e. behind sign-like steps that amplify the atomic-order
+        # noise of the bilinear scatter: it gets the trajectory floor (measured on B200 at the first replay: lossD 3e-6, lossG 3.6e-4).
+        tolD = 1e-4 if i < 3 else 5e-3
+        assert abs(e[i][0] - r[i][0]) < tolD and abs(e[i][1] - r[i][1]) < 5e-3, (i, e[i][:2], r[i][:2])
+        assert np.abs(e[i][2] - r[i][2]).max() < max(tolD, 1e-3)
         assert r[i][3] == e[i][3] > 500, "replay accounts for the same number of kernel launches as the eager step"
     assert len({round(x[0], 6) for x in r}) == 6, "every replay sees new dropout masks and a new Adam step (losses differ)"
     assert np.mean(np.abs(out[0][1] - out[1][1]) > 0.5e-3) < 2e-2 and np.mean(np.abs(out[0][2] - out[1][2]) > 0.5e-3) < 2e-2

@@ -60,6 +60,7 @@ void prof_end() { cudaEventRecord(ctx().prof.back().b, ctx().stream); }
 void* workspace(size_t bytes) { return grow(&ctx().ws, &ctx().ws_bytes, bytes); }
 void* workspace2(size_t bytes) { return grow(&ctx().ws2, &ctx().ws2_bytes, bytes); }
 void* workspace3(size_t bytes) { return grow(&ctx().ws3, &ctx().ws3_bytes, bytes); }
+void* workspace4(size_t bytes) { return grow(&ctx().ws4, &ctx().ws4_bytes, bytes); }
 void* pinned(size_t bytes) {
   Ctx& c = ctx();
   if (c.pinned_bytes >= bytes && c.pinned) return c.pinned;
@@ -126,8 +127,8 @@ void cg_shutdown(void) {
 #ifdef CG_WITH_NCCL
   if (c.nccl && nccl_api().ok) { nccl_api().CommDestroy((ncclComm_t)c.nccl); c.nccl = nullptr; }
 #endif
-  if (c.ws) cudaFree(c.ws); if (c.ws2) cudaFree(c.ws2); if (c.ws3) cudaFree(c.ws3); if (c.pinned) cudaFreeHost(c.pinned);
-  c.ws = c.ws2 = c.ws3 = c.pinned = nullptr; c.ws_bytes = c.ws2_bytes = c.ws3_bytes = c.pinned_bytes = 0;
+  if (c.ws) cudaFree(c.ws); if (c.ws2) cudaFree(c.ws2); if (c.ws3) cudaFree(c.ws3); if (c.ws4) cudaFree(c.ws4); if (c.pinned) cudaFreeHost(c.pinned);
+  c.ws = c.ws2 = c.ws3 = c.ws4 = c.pinned = nullptr; c.ws_bytes = c.ws2_bytes = c.ws3_bytes = c.ws4_bytes = c.pinned_bytes = 0;
   cudaStreamDestroy(c.stream); c.stream = nullptr; c.inited = false; c.device = -1; c.world = 1; c.rank = 0;
 }
 const char* cg_last_error(void) { return ctx().err; }

@@ -25,6 +25,7 @@ struct Ctx {
   void* ws = nullptr; size_t ws_bytes = 0;
   void* ws2 = nullptr; size_t ws2_bytes = 0;
   void* ws3 = nullptr; size_t ws3_bytes = 0;
+  void* ws4 = nullptr; size_t ws4_bytes = 0;
   void* pinned = nullptr; size_t pinned_bytes = 0;
   // data parallel
   int rank = 0, world = 1;
@@ -45,6 +46,7 @@ void* workspace(size_t bytes);    // device scratch #1 (split-K partials, reduct
 void* workspace2(size_t bytes);   // device scratch #2: boundary staging of the host-pointer entry points ONLY
 void* workspace3(size_t bytes);   // device scratch #3: tensor-core operand packing (never shared with staging: a grow
                                   // reallocates, and ws2 pointers are live across the whole forward/backward call)
+void* workspace4(size_t bytes);   // device scratch #4: the packed gradient operand shared by dgrad and wgrad of one layer (outlives both runs' ws3 use)
 void* pinned(size_t bytes);       // pinned host staging
 
 #define CG_CUDA(expr)                                                                         \

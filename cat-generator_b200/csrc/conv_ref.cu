@@ -265,6 +265,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
 // conv_tc.cu provides these; they return CG_ERR_UNSUPPORTED for shapes the tensor-core path does not take.
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k);
 void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valued inputs (tools/backward_precision_study.py)
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
@@ -281,6 +282,13 @@ int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W,
 int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
   if (ctx().conv_engine == 1) { int s = conv_wgrad_tc(x, gy, gWp_out, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
   return conv_wgrad_ref(x, gy, gWp_out, N, H, W, Ci, Co, k);
+}
+
+// weight gradient + input gradient of one layer; the tensor-core engine packs the gradient operand once for both
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k) {
+  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
+  CG_TRY(conv_wgrad(x, gy, gWp_out, N, H, W, Ci, Co, k));
+  return conv_dgrad(gy, Wd, gx, N, H, W, Ci, Co, k);
 }
 
 }  // namespace cg

@@ -353,7 +353,8 @@ static bool tc_shape_ok(int H, int W, int Ci, int Co, int k, int ES) {
 }
 
 template <int ES>
-static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr) {
+static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
+                       const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
   constexpr int PER = 16 / ES, KB = 128 / ES;
   const int Ci = ((Cir + KB - 1) / KB) * KB, Co = ((Cor + 15) / 16) * 16;   // padded sizes the kernel iterates over
   const int p = (k - 1) / 2, kk = k * k;
@@ -380,11 +381,12 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   size_t smem = 2 * TL * patch_bytes + (size_t)S * slice_bytes;
   // operand buffers: activations then weight slices (16-byte aligned)
   size_t xq_bytes = (size_t)N * (Ci / PER) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * ES;
-  uint8_t* ws = (uint8_t*)workspace3(xq_bytes + wq_bytes + 256);
+  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : xq_bytes) + wq_bytes + 512);
   if (!ws) return CG_ERR_CUDA;
-  uint8_t* xq = ws; uint8_t* wq = ws + ((xq_bytes + 255) & ~(size_t)255);
+  const uint8_t* xq = xq_prepacked ? xq_prepacked : ws;
+  uint8_t* wq = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
-  CG_LAUNCH(k_pack_act<ES>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Cir, Ci, p, Hq, Wq, scale2);
+  if (!xq_prepacked) CG_LAUNCH(k_pack_act<ES>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2);
   CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk, CB);
   P.xq = xq; P.wq = wq; P.bias = bias; P.y = y; P.scale2 = scale2;
   P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
@@ -420,19 +422,34 @@ static float* tc_scale_scratch() {   // [scale, 1/scale, amax bits]: its own all
   return p;
 }
 
+// ONE packed gradient operand per layer: gq[N][Cg/8][Hq][Wq][8] fp16, zero-padded by the filter radius, channels padded to 64,
+// multiplied by the per-tensor power of two.  dgrad reads halo'd patches from it (A operand), wgrad reads 16x8-pixel tiles
+// from it (B operand) through a second tensor map.  Before this, gy was read three times per layer (absmax, tf32 pack, fp16 tile pack).
+struct GradOperand { const uint8_t* gq; const float* scale2; int Cg; };
+static int pack_grad_operand(const float* gy, int N, int H, int W, int C, int k, GradOperand* out) {
+  const int p = (k - 1) / 2, Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Cg = ((C + 63) / 64) * 64;
+  float* sc = tc_scale_scratch(); if (!sc) return set_err(CG_ERR_CUDA, "scale scratch allocation failed");
+  unsigned int* amax = (unsigned int*)(sc + 2);
+  size_t bytes = (size_t)N * (Cg / 8) * Hq * Wq * 16;
+  uint8_t* gq = (uint8_t*)workspace4(bytes + 256); if (!gq) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
+  long n = (long)N * H * W * C;
+  CG_LAUNCH(k_absmax, grid1d(n, 256, 8), 256, 0, gy, n, amax);
+  CG_LAUNCH(k_make_scale, 1, 1, 0, amax, sc);
+  long nq = (long)(bytes / 16);
+  CG_LAUNCH(k_pack_act<2>, grid1d(nq, 256), 256, 0, gy, gq, nq, H, W, C, Cg, p, Hq, Wq, (const float*)sc);
+  out->gq = gq; out->scale2 = sc; out->Cg = Cg;
+  return CG_OK;
+}
+
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
   if (!tc_shape_ok(H, W, Ci, Co, k, 2)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return CG_ERR_UNSUPPORTED;
   if (!g_tc_grad_operands) return conv_tc_run<2>(x, Wp, bias, y, N, H, W, Ci, Co, k);
   if (dgrad_tf32) return conv_tc_run<4>(x, Wp, bias, y, N, H, W, Ci, Co, k);
-  float* sc = tc_scale_scratch(); if (!sc) return set_err(CG_ERR_CUDA, "scale scratch allocation failed");
-  unsigned int* amax = (unsigned int*)(sc + 2);
-  CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
-  long n = (long)N * H * W * Ci;
-  CG_LAUNCH(k_absmax, grid1d(n, 256, 8), 256, 0, x, n, amax);
-  CG_LAUNCH(k_make_scale, 1, 1, 0, amax, sc);
-  return conv_tc_run<2>(x, Wp, bias, y, N, H, W, Ci, Co, k, sc);
+  GradOperand g; CG_TRY(pack_grad_operand(x, N, H, W, Ci, k, &g));
+  return conv_tc_run<2>(x, Wp, bias, y, N, H, W, Ci, Co, k, g.scale2, g.gq);
 }
 
 // =================================================================== weight gradient on the tensor cores
@@ -459,34 +476,6 @@ __global__ void k_make_scale(const unsigned int* __restrict__ amax, float* __res
   if (!(sc > 0.f) || !isfinite(sc)) sc = 1.f;
   scale2[0] = sc; scale2[1] = 1.f / sc;
 }
-// gy NHWC fp32 -> gq[n][ty][tx][Co/8][16][8][8] fp16, scaled, rows >= H zero
-__global__ void k_pack_gtile(const float* __restrict__ gy, uint8_t* __restrict__ gq, const float* __restrict__ scale2, long nchunks,
-                             int H, int W, int Co, int Cop, int tiles_x, int tiles_y) {
-  float sc = scale2[0];
-  int Cq = Cop / 8;
-  const bool fast = (Co & 7) == 0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
-    int px = (int)(i & 7); long t = i >> 3; int r = (int)(t & 15); t >>= 4; int c = (int)(t % Cq); t /= Cq;
-    int tx = (int)(t % tiles_x); t /= tiles_x; int ty = (int)(t % tiles_y); long n = t / tiles_y;
-    int y = ty * 16 + r, x = tx * 8 + px;
-    uint4 out = make_uint4(0, 0, 0, 0);
-    if (y < H && c * 8 < Co) {
-      const float* s = gy + ((n * H + y) * W + x) * Co + c * 8;
-      float4 a, b;
-      if (fast) { a = *reinterpret_cast<const float4*>(s); b = *reinterpret_cast<const float4*>(s + 4); }
-      else {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c * 8 + j < Co) ? s[j] : 0.f;
-        a = make_float4(v[0], v[1], v[2], v[3]); b = make_float4(v[4], v[5], v[6], v[7]);
-      }
-      __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc), h2 = __floats2half2_rn(b.x * sc, b.y * sc), h3 = __floats2half2_rn(b.z * sc, b.w * sc);
-      out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
-    }
-    reinterpret_cast<uint4*>(gq)[i] = out;
-  }
-}
-
 struct TcWParams {
   const uint8_t* xq; const uint8_t* gq; float* part; const float* scale2;
   int N, H, W, Ci, Co, k, p, Hq, Wq;   // Ci/Co: PADDED counts (operand addressing)
@@ -496,7 +485,7 @@ struct TcWParams {
   uint32_t patch_bytes, patch_load_bytes, g_bytes;
 };
 
-__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_constant__ CUtensorMap tmx) {
+__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmg) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -510,7 +499,6 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
   const int tap0 = tg * P.TG, kk = P.k * P.k;
   const int ntap = (tap0 + P.TG <= kk) ? P.TG : (kk - tap0);
   const long t0 = (long)P.tiles_total * z / P.Z, t1 = (long)P.tiles_total * (z + 1) / P.Z;
-  const int Gq = P.Co / 8;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
@@ -535,13 +523,14 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 4) {
-    if (lane == 0) {   // gy tiles: one bulk copy each
+    if (lane == 0) {   // gy tiles: one tiled TMA each, [NB/8 planes][16 rows][8 px][16 B] out of the shared blocked operand
       int it = 0;
       for (long t = t0; t < t1; ++t, ++it) {
         int buf = it & 1;
+        int tx = (int)(t % P.tiles_x); long q = t / P.tiles_x; int ty = (int)(q % P.tiles_y); int n = (int)(q / P.tiles_y);
         mbar_wait(&bar_empty[buf], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&bar_full[buf], P.g_bytes);
-        bulk_g2s(smem + (size_t)buf * stage_bytes + P.patch_bytes, P.gq + ((size_t)t * Gq + (size_t)cob * (P.NB / 8)) * 2048, P.g_bytes, &bar_full[buf]);
+        tma_patch_4d(smem + (size_t)buf * stage_bytes + P.patch_bytes, &tmg, (tx * 8 + P.p) * 8, ty * 16 + P.p, cob * (P.NB / 8), n, &bar_full[buf]);
       }
     }
   } else if (warp == 5) {   // x patches: ONE tiled TMA per tile
@@ -633,11 +622,23 @@ __global__ void k_sum_parts(const float* __restrict__ part, int Z, long n, float
   }
 }
 
-int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
+// tile map of the blocked gradient operand: box = 8 px x 16 rows x planes
+static int make_tile_tmap(CUtensorMap* tm, const void* gq, int N, int Cq, int Hq, int Wq, int planes) {
+  cg_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {(cuuint64_t)Wq * 8, (cuuint64_t)Hq, (cuuint64_t)Cq, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Wq * 16, (cuuint64_t)Hq * Wq * 16, (cuuint64_t)Cq * Hq * Wq * 16};
+  cuuint32_t box[4] = {64, 16, (cuuint32_t)planes, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(gq), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled (gradient tiles) failed with %d", (int)r);
+  return CG_OK;
+}
+static bool wgrad_shape_ok(int H, int W, int Cir, int k) { return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && (Cir <= 64 || Cir % 128 == 0); }
+
+static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
   // Cin <= 64 is zero-padded to 64 (rows 64..127 of the M = 128 instruction read zero planes); Cout is padded to 16
-  if (!((k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && (Cir <= 64 || Cir % 128 == 0))) return CG_ERR_UNSUPPORTED;
   const int Ci = Cir <= 64 ? 64 : Cir, Co = ((Cor + 15) / 16) * 16;
-  if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out) & 15) != 0) return CG_ERR_UNSUPPORTED;
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
   TcWParams P{};
@@ -659,31 +660,46 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
   int base = P.ncib * P.ncob * P.ntg;
   int Z = (ctx().sm_count + base - 1) / base; if (Z > P.tiles_total / 2) Z = P.tiles_total / 2; if (Z < 1) Z = 1;
   P.Z = Z;
-  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, gq_bytes = (size_t)P.tiles_total * (Co / 8) * 2048;
+  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16;
   size_t part_bytes = (size_t)Z * kk * Cir * Cor * sizeof(float);
-  size_t o1 = (xq_bytes + 255) & ~(size_t)255, o2 = o1 + ((gq_bytes + 255) & ~(size_t)255), o3 = o2 + ((part_bytes + 255) & ~(size_t)255);
-  uint8_t* ws = (uint8_t*)workspace3(o3 + 256);
+  size_t o1 = (xq_bytes + 255) & ~(size_t)255;
+  uint8_t* ws = (uint8_t*)workspace3(o1 + part_bytes + 512);
   if (!ws) return CG_ERR_CUDA;
-  uint8_t* xq = ws; uint8_t* gq = ws + o1; float* part = (float*)(ws + o2); float* scale2 = (float*)(ws + o3); unsigned int* amax = (unsigned int*)(scale2 + 2);
-  CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
-  long ng = (long)N * H * W * Cor;
-  CG_LAUNCH(k_absmax, grid1d(ng, 256, 8), 256, 0, gy, ng, amax);
-  CG_LAUNCH(k_make_scale, 1, 1, 0, amax, scale2);
-  long nx = (long)(xq_bytes / 16), ngq = (long)(gq_bytes / 16);
+  uint8_t* xq = ws; float* part = (float*)(ws + o1);
+  long nx = (long)(xq_bytes / 16);
   CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Cir, Ci, p, Hq, Wq, (const float*)nullptr);
-  CG_LAUNCH(k_pack_gtile, grid1d(ngq, 256), 256, 0, gy, gq, scale2, ngq, H, W, Cor, Co, P.tiles_x, P.tiles_y);
-  P.xq = xq; P.gq = gq; P.part = part; P.scale2 = scale2;
+  P.xq = xq; P.gq = g.gq; P.part = part; P.scale2 = g.scale2;
   static bool attr_done = false;
   if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
   dim3 grid(Z, base);
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;   // algorithmic (unpadded) work
-  ctx().next_bytes = (double)xq_bytes + (double)gq_bytes + 4.0 * (double)kk * Cir * Cor;
-  CUtensorMap tmx;
+  ctx().next_bytes = (double)xq_bytes + (double)N * (g.Cg / 8) * Hq * Wq * 16 + 4.0 * (double)kk * Cir * Cor;
+  CUtensorMap tmx, tmg;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, P.cim / 8));
-  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx);
+  CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
+  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
   CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
   return CG_OK;
+}
+
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
+  if (!wgrad_shape_ok(H, W, Cir, k)) return CG_ERR_UNSUPPORTED;
+  if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out) & 15) != 0) return CG_ERR_UNSUPPORTED;
+  GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Cor, k, &g));
+  return conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Cir, Cor, k);
+}
+
+// Whole backward of one conv layer: weight gradient AND input gradient from ONE packed gradient operand.
+//   gWp_out[(tap,ci)][co] (overwritten) ; gx[N,H,W,Ci] = conv(gy, Wd)
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k) {
+  static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
+  if (dgrad_tf32 || !wgrad_shape_ok(H, W, Ci, k) || !tc_shape_ok(H, W, Co, Ci, k, 2)) return CG_ERR_UNSUPPORTED;
+  if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out | (uintptr_t)gx) & 15) != 0) return CG_ERR_UNSUPPORTED;
+  GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g));
+  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k));
+  // dgrad = forward convolution of gy (Co channels in) with the flipped weights (Ci channels out)
+  return conv_tc_run<2>(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k, g.scale2, g.gq);
 }
 
 }  // namespace cg

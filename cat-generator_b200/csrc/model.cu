@@ -173,14 +173,14 @@ static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H
 static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W) {
   cg_layer& L = m->layers[li];
   long M = (long)N * H * W;
-  CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k));
+  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k));
+  else CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k));
   CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
   if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
   else {
     float* tmp = m->gwp.p;   // wgrad scratch is free again (stream ordered)
     CG_TRY(fill(tmp, 0.f, L.s.Co)); CG_TRY(colsum_acc(gy, tmp, M, L.s.Co)); CG_TRY(unpack_bias_acc(tmp, m->G + L.ob, L.s));
   }
-  if (gx) CG_TRY(conv_dgrad(gy, L.Wd, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k));
   return CG_OK;
 }
 

@@ -74,5 +74,7 @@ int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N
 int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k);
 // gWp_out[(ky,kx,ci)][co] = sum_pixels x[p+tap,ci]*gy[p,co]  (overwritten, packed layout)
 int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+// both gradients of one layer (gWp_out overwritten, gx written)
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k);
 
 }  // namespace cg

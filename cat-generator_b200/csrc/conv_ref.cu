@@ -63,6 +63,42 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, int S, long n, i
   }
 }
 
+// ------------------------------------------------------------------ partial sums -> Torch-layout gradient, fused
+// gW[co][ci][ky][kx] += sum_z part[z][(tap,ci)][co].  A block takes all taps of CIB input channels x 32 output channels: the packed
+// partials are read coalesced along co and summed in fixed z order (deterministic), transposed through shared memory, and each
+// output channel's [ci][tap] run is written contiguously.  Replaces k_sum_parts / k_splitk_reduce + k_unpack_wgrad, whose
+// strided read-modify-write (stride k*k floats) was 1.5 ms of a 10 ms step (profiles/r01_bench_tc_engine.json).
+__global__ void __launch_bounds__(256) k_parts_to_torch_acc(const float* __restrict__ part, int Z, long zstride, float* __restrict__ gW,
+                                                            int Ci, int Co, int kk, int CIB) {
+  __shared__ float t[6600];                       // kk * CIB * 33 <= 25*8*33 = 6600 (k = 7 uses CIB = 4: 49*4*33 = 6468)
+  const int ci0 = blockIdx.x * CIB, co0 = blockIdx.y * 32, tid = threadIdx.x;
+  const int nload = kk * CIB * 32;
+  for (int i = tid; i < nload; i += 256) {
+    int col = i & 31, r = i >> 5, cil = r % CIB, tap = r / CIB;
+    int ci = ci0 + cil, co = co0 + col;
+    float sum = 0.f;
+    if (ci < Ci && co < Co) {
+      const float* src = part + ((long)tap * Ci + ci) * Co + co;
+      for (int z = 0; z < Z; ++z) sum += src[(long)z * zstride];
+    }
+    t[(tap * CIB + cil) * 33 + col] = sum;
+  }
+  __syncthreads();
+  const int run = CIB * kk;                        // contiguous floats per output channel in the Torch layout
+  for (int i = tid; i < 32 * run; i += 256) {
+    int col = i / run, r = i - col * run, cil = r / kk, tap = r - cil * kk;
+    int ci = ci0 + cil, co = co0 + col;
+    if (ci < Ci && co < Co) gW[((long)co * Ci + ci) * kk + tap] += t[(tap * CIB + cil) * 33 + col];   // accGradParameters adds
+  }
+}
+int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk) {
+  int CIB = kk <= 25 ? 8 : 4;
+  if (kk * CIB * 33 > 6600) return CG_ERR_UNSUPPORTED;
+  dim3 g(cdiv(Ci, CIB), cdiv(Co, 32));
+  CG_LAUNCH(k_parts_to_torch_acc, g, 256, 0, part, Z, zstride, gW_acc, Ci, Co, kk, CIB);
+  return CG_OK;
+}
+
 // ------------------------------------------------------------------ forward / dgrad: C[M=pixels, Co] = A[M, K=(tap,ci)] * Wp[K, Co]
 constexpr int BM = 64, BN = 64, BK = 16;
 template <bool VEC>
@@ -244,7 +280,7 @@ __global__ void __launch_bounds__(256) k_conv_wgrad(const float* __restrict__ x,
   }
 }
 
-static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
+static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
   long M = (long)N * H * W; int Ktot = k * k * Ci;
   int tiles = cdiv(Ktot, BM) * cdiv(Co, BN);
   int target = ctx().sm_count * 3;
@@ -257,6 +293,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
   ctx().next_flops = 2.0 * (double)M * Co * Ktot; ctx().next_bytes = 4.0 * ((double)M * Ci + (double)M * Co + (double)Ktot * Co);
   if (vec) CG_LAUNCH(k_conv_wgrad<true>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
   else CG_LAUNCH(k_conv_wgrad<false>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
+  if (gW_acc && parts_to_torch_acc(dst, S, (long)Ktot * Co, gW_acc, Ci, Co, k * k) == CG_OK) { if (done) *done = 1; return CG_OK; }
   if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out); }
   return CG_OK;
 }
@@ -264,8 +301,8 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
 // ------------------------------------------------------------------ engine dispatch
 // conv_tc.cu provides these; they return CG_ERR_UNSUPPORTED for shapes the tensor-core path does not take.
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
-int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
-int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k);
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done);
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done);
 void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valued inputs (tools/backward_precision_study.py)
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
@@ -279,15 +316,18 @@ int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W,
   conv_tc_set_gradient_operands(0);
   return s;
 }
-int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k) {
-  if (ctx().conv_engine == 1) { int s = conv_wgrad_tc(x, gy, gWp_out, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
-  return conv_wgrad_ref(x, gy, gWp_out, N, H, W, Ci, Co, k);
+// gW_acc (optional): Torch-layout gradient [Co][Ci][k][k] of a plain conv; when the engine could add into it directly *done = 1
+// and gWp_out is left untouched, otherwise gWp_out holds the packed gradient and the caller unpacks.
+int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
+  if (done) *done = 0;
+  if (ctx().conv_engine == 1) { int s = conv_wgrad_tc(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done); if (s != CG_ERR_UNSUPPORTED) return s; }
+  return conv_wgrad_ref(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done);
 }
-
 // weight gradient + input gradient of one layer; the tensor-core engine packs the gradient operand once for both
-int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k) {
-  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
-  CG_TRY(conv_wgrad(x, gy, gWp_out, N, H, W, Ci, Co, k));
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
+  if (done) *done = 0;
+  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k, gW_acc, done); if (s != CG_ERR_UNSUPPORTED) return s; }
+  CG_TRY(conv_wgrad(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done));
   return conv_dgrad(gy, Wd, gx, N, H, W, Ci, Co, k);
 }
 

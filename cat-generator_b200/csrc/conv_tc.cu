@@ -636,7 +636,7 @@ static int make_tile_tmap(CUtensorMap* tm, const void* gq, int N, int Cq, int Hq
 }
 static bool wgrad_shape_ok(int H, int W, int Cir, int k) { return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && (Cir <= 64 || Cir % 128 == 0); }
 
-static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
+static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k, float* gW_acc, int* done) {
   // Cin <= 64 is zero-padded to 64 (rows 64..127 of the M = 128 instruction read zero planes); Cout is padded to 16
   const int Ci = Cir <= 64 ? 64 : Cir, Co = ((Cor + 15) / 16) * 16;
   const int p = (k - 1) / 2, kk = k * k;
@@ -679,25 +679,26 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
   CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
+  if (gW_acc && parts_to_torch_acc(part, Z, nW, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; return CG_OK; }
   CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
   return CG_OK;
 }
 
-int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k) {
+int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k, float* gW_acc, int* done) {
   if (!wgrad_shape_ok(H, W, Cir, k)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out) & 15) != 0) return CG_ERR_UNSUPPORTED;
   GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Cor, k, &g));
-  return conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Cir, Cor, k);
+  return conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Cir, Cor, k, gW_acc, done);
 }
 
 // Whole backward of one conv layer: weight gradient AND input gradient from ONE packed gradient operand.
 //   gWp_out[(tap,ci)][co] (overwritten) ; gx[N,H,W,Ci] = conv(gy, Wd)
-int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k) {
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
   if (dgrad_tf32 || !wgrad_shape_ok(H, W, Ci, k) || !tc_shape_ok(H, W, Co, Ci, k, 2)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out | (uintptr_t)gx) & 15) != 0) return CG_ERR_UNSUPPORTED;
   GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g));
-  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k));
+  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done));
   // dgrad = forward convolution of gy (Co channels in) with the flipped weights (Ci channels out)
   return conv_tc_run<2>(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k, g.scale2, g.gq);
 }

@@ -173,9 +173,12 @@ static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H
 static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W) {
   cg_layer& L = m->layers[li];
   long M = (long)N * H * W;
-  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k));
-  else CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k));
-  CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
+  // plain convolutions let the engine add straight into the Torch-layout gradient; Linear layers beside an nn.View need the permuting unpack
+  float* gW_direct = (L.s.in_hw == 1 && L.s.out_hw == 1) ? m->G + L.oW : nullptr;
+  int direct = 0;
+  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
+  else CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
+  if (!direct) CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
   if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
   else {
     float* tmp = m->gwp.p;   // wgrad scratch is free again (stream ordered)

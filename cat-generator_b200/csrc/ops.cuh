@@ -73,8 +73,10 @@ int unpack_bias_acc(const float* gbp, float* gb_acc, const ConvSpec& s);
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k);
 // gWp_out[(ky,kx,ci)][co] = sum_pixels x[p+tap,ci]*gy[p,co]  (overwritten, packed layout)
-int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k);
+// gW_acc/done: optional direct accumulation into the Torch-layout gradient of a plain conv (see conv_ref.cu)
+int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr);
+int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk);
 // both gradients of one layer (gWp_out overwritten, gx written)
-int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k);
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr);
 
 }  // namespace cg

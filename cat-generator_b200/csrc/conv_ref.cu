@@ -91,8 +91,11 @@ __global__ void __launch_bounds__(256) k_parts_to_torch_acc(const float* __restr
     if (ci < Ci && co < Co) gW[((long)co * Ci + ci) * kk + tap] += t[(tap * CIB + cil) * 33 + col];   // accGradParameters adds
   }
 }
+// NOTE (measured): calling this with Z > 1 made it the slowest kernel of the step (5.2 ms): with ~128 blocks each thread walked
+// ~275 partial-sum loads megabytes apart, serially.  Callers therefore reduce the partials first with the fully parallel
+// element-wise kernels (k_sum_parts / k_splitk_reduce) and use this kernel with Z = 1 for the layout change only.
 int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk) {
-  int CIB = kk <= 25 ? 8 : 4;
+  int CIB = kk <= 9 ? 8 : (kk <= 25 ? 4 : 2);     // smaller channel blocks for big filters: more blocks, runs of >= 98 floats
   if (kk * CIB * 33 > 6600) return CG_ERR_UNSUPPORTED;
   dim3 g(cdiv(Ci, CIB), cdiv(Co, 32));
   CG_LAUNCH(k_parts_to_torch_acc, g, 256, 0, part, Z, zstride, gW_acc, Ci, Co, kk, CIB);
@@ -293,8 +296,8 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
   ctx().next_flops = 2.0 * (double)M * Co * Ktot; ctx().next_bytes = 4.0 * ((double)M * Ci + (double)M * Co + (double)Ktot * Co);
   if (vec) CG_LAUNCH(k_conv_wgrad<true>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
   else CG_LAUNCH(k_conv_wgrad<false>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
-  if (gW_acc && parts_to_torch_acc(dst, S, (long)Ktot * Co, gW_acc, Ci, Co, k * k) == CG_OK) { if (done) *done = 1; return CG_OK; }
   if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out); }
+  if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Ci, Co, k * k) == CG_OK) { if (done) *done = 1; }
   return CG_OK;
 }
 

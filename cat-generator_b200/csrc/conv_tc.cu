@@ -679,8 +679,8 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
   CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
-  if (gW_acc && parts_to_torch_acc(part, Z, nW, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; return CG_OK; }
-  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);
+  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // fully parallel, fixed z order
+  if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; }   // layout change only
   return CG_OK;
 }
 

@@ -383,11 +383,13 @@ static int read_losses(cg_trainer* t, const cg_step_cfg* c, float* lossD, float*
 // The step as the caller sees it: eager for the first calls of a configuration (every buffer reaches its final size, function
 // attributes are set), then captured once into a CUDA graph and replayed.  A step is ~1200 small launches and the per-launch
 // cost dominated it (profiles/r01_bench_tc_engine.json); everything a replay needs -- Adam's step count, the dropout RNG
-// offset -- lives in device memory.  Never captured: profiling runs, multi-rank runs (NCCL stays eager), forwards that consume
-// masks queued by cg_D_set_masks.  A failed capture disables graphs for that configuration and the step runs eagerly.
+// offset -- lives in device memory.  Never captured: profiling runs and forwards that consume masks queued by cg_D_set_masks.  A failed capture disables graphs for that configuration and the step runs eagerly.
 static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real, const float* zD, const float* zG, float* lossD, float* lossG) {
   Ctx& X = ctx();
-  bool eligible = X.graph_mode && !X.prof_on && X.world == 1 && !(t->D->mq && t->D->mq_next < t->D->mq_count);
+  // Multi-rank steps are captured too (the two NCCL all-reduces become graph nodes; NCCL >= 2.9 supports stream capture): every
+  // rank captures at the same call number, so the collectives inside the capture line up.  Keeping N > 1 eager made data
+  // parallel look ~25% worse than N = 1 for a reason unrelated to communication.
+  bool eligible = X.graph_mode && !X.prof_on && !(t->D->mq && t->D->mq_next < t->D->mq_count);
   if (!eligible) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   cg_trainer::StepGraph* sg = nullptr;
   for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg))) { sg = &e; break; }

@@ -305,7 +305,8 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
 // conv_tc.cu provides these; they return CG_ERR_UNSUPPORTED for shapes the tensor-core path does not take.
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done);
-int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done);
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
+                const uint8_t* xq_prepacked);
 void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valued inputs (tools/backward_precision_study.py)
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
@@ -327,9 +328,12 @@ int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, in
   return conv_wgrad_ref(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done);
 }
 // weight gradient + input gradient of one layer; the tensor-core engine packs the gradient operand once for both
-int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
+// xq (optional): the forward's cached fp16 operand for x; then x may be null and only the tensor-core engine can serve the call
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
+                  const uint8_t* xq) {
   if (done) *done = 0;
-  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k, gW_acc, done); if (s != CG_ERR_UNSUPPORTED) return s; }
+  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k, gW_acc, done, xq); if (s != CG_ERR_UNSUPPORTED) return s; }
+  if (!x) return set_err(CG_ERR_STATE, "this forward cached only the tensor-core operand of the layer input; backward needs the same conv engine");
   CG_TRY(conv_wgrad(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done));
   return conv_dgrad(gy, Wd, gx, N, H, W, Ci, Co, k);
 }

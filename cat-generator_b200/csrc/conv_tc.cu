@@ -96,6 +96,42 @@ __device__ __forceinline__ void umma(uint32_t tmem, uint64_t ad, uint64_t bd, ui
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
 
+// Fused producer of a conv layer's fp16 operand inside G:  y = PReLU(BN(x))  ->  nearest 2x upsample  ->  blocked/padded fp16
+// (the k_pack_act<2> layout).  One pass over the conv output instead of four (BN apply, PReLU, upsample, pack), and the fp32
+// PReLU output and its upsampled copy are never materialised: the packed operand is what both this layer's forward and its
+// weight gradient read.  bn (PReLU's input, needed by PReLU's backward) is written once per source element when asked for.
+// mean == nullptr: no batch norm (the stage after nn.Linear).  Arithmetic order matches k_bn_apply / k_prelu_fwd.
+__global__ void k_bn_prelu_up_pack(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ pw,
+                                   float* __restrict__ bn_out, uint8_t* __restrict__ xq, long nchunks, int h, int w, int C, int up, int p, int Hq, int Wq) {
+  const int Cq = C / 8, H = h << up, W = w << up;
+  const float a = *pw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
+    int xx = (int)(i % Wq); long t = i / Wq; int yy = (int)(t % Hq); t /= Hq; int c = (int)(t % Cq); long n = t / Cq;
+    int iy = yy - p, ix = xx - p;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      long off = ((n * h + (iy >> up)) * w + (ix >> up)) * C + c * 8;
+      float4 v0 = *reinterpret_cast<const float4*>(x + off), v1 = *reinterpret_cast<const float4*>(x + off + 4);
+      float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      if (mean) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { int cc = c * 8 + j; v[j] = (v[j] - mean[cc]) * invstd[cc] * gamma[cc] + beta[cc]; }
+        if (bn_out && (!up || (((iy | ix) & 1) == 0))) {
+          *reinterpret_cast<float4*>(bn_out + off) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(bn_out + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : a * v[j];
+      __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]), h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+      out.x = *reinterpret_cast<uint32_t*>(&h0); out.y = *reinterpret_cast<uint32_t*>(&h1); out.z = *reinterpret_cast<uint32_t*>(&h2); out.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    reinterpret_cast<uint4*>(xq)[i] = out;
+  }
+}
+
+
 // ------------------------------------------------------------------ operand packing
 // Activations: NHWC fp32 -> channel-blocked, zero-padded xq[N][Ci/PER][Hq][Wq][PER] (PER*ES = 16 bytes),
 // Hq = roundup(H,16) + 2p, Wq = W + 2p, image at offset (p,p).  Rounding: RN to fp16 / RN to tf32.
@@ -442,6 +478,30 @@ static int pack_grad_operand(const float* gy, int N, int H, int W, int C, int k,
   return CG_OK;
 }
 
+// ---- cached operand path (G's stages): the producer above writes the operand once, forward and weight gradient both read it.
+// The forward operand (Cin padded to 64) and the weight-gradient operand (Cin 64 or a multiple of 128) must be the same buffer.
+bool conv_tc_cached_ok(int H, int W, int Ci, int Co, int k) {
+  static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
+  return !dgrad_tf32 && (Ci == 64 || Ci % 128 == 0) && tc_shape_ok(H, W, Ci, Co, k, 2) && tc_shape_ok(H, W, Co, Ci, k, 2);   // implies wgrad_shape_ok
+}
+size_t conv_tc_operand_bytes(int N, int H, int W, int Ci, int k) {
+  const int p = (k - 1) / 2;
+  return (size_t)N * (Ci / 8) * (((H + 15) / 16) * 16 + 2 * p) * (W + 2 * p) * 16;
+}
+// x: [N,h,w,C] conv output (or the Linear output viewed NHWC); operand for a k x k conv on the (h<<up) x (w<<up) image
+int bn_prelu_up_pack(const float* x, const float* gamma, const float* beta, const float* mean, const float* invstd, const float* pw,
+                     float* bn_out, uint8_t* xq, int N, int h, int w, int C, int up, int k) {
+  const int p = (k - 1) / 2, H = h << up, W = w << up;
+  const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p;
+  long n = (long)N * (C / 8) * Hq * Wq;
+  ctx().next_bytes = 4.0 * N * h * w * C * (bn_out ? 2 : 1) + 16.0 * n;
+  CG_LAUNCH(k_bn_prelu_up_pack, grid1d(n, 256), 256, 0, x, gamma, beta, mean, invstd, pw, bn_out, xq, n, h, w, C, up, p, Hq, Wq);
+  return CG_OK;
+}
+int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
+  return conv_tc_run<2>(nullptr, Wp, bias, y, N, H, W, Ci, Co, k, nullptr, xq);
+}
+
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
   if (!tc_shape_ok(H, W, Ci, Co, k, 2)) return CG_ERR_UNSUPPORTED;
@@ -636,7 +696,8 @@ static int make_tile_tmap(CUtensorMap* tm, const void* gq, int N, int Cq, int Hq
 }
 static bool wgrad_shape_ok(int H, int W, int Cir, int k) { return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0 && (Cir <= 64 || Cir % 128 == 0); }
 
-static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k, float* gW_acc, int* done) {
+static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_out, int N, int H, int W, int Cir, int Cor, int k, float* gW_acc, int* done,
+                              const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the forward's cached operand (bn_prelu_up_pack)
   // Cin <= 64 is zero-padded to 64 (rows 64..127 of the M = 128 instruction read zero planes); Cout is padded to 16
   const int Ci = Cir <= 64 ? 64 : Cir, Co = ((Cor + 15) / 16) * 16;
   const int p = (k - 1) / 2, kk = k * k;
@@ -662,12 +723,12 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   P.Z = Z;
   size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16;
   size_t part_bytes = (size_t)Z * kk * Cir * Cor * sizeof(float);
-  size_t o1 = (xq_bytes + 255) & ~(size_t)255;
+  size_t o1 = xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255);
   uint8_t* ws = (uint8_t*)workspace3(o1 + part_bytes + 512);
   if (!ws) return CG_ERR_CUDA;
-  uint8_t* xq = ws; float* part = (float*)(ws + o1);
+  const uint8_t* xq = xq_prepacked ? xq_prepacked : ws; float* part = (float*)(ws + o1);
   long nx = (long)(xq_bytes / 16);
-  CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, xq, nx, H, W, Cir, Ci, p, Hq, Wq, (const float*)nullptr);
+  if (!xq_prepacked) CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, (const float*)nullptr);
   P.xq = xq; P.gq = g.gq; P.part = part; P.scale2 = g.scale2;
   static bool attr_done = false;
   if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
@@ -693,12 +754,14 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
 
 // Whole backward of one conv layer: weight gradient AND input gradient from ONE packed gradient operand.
 //   gWp_out[(tap,ci)][co] (overwritten) ; gx[N,H,W,Ci] = conv(gy, Wd)
-int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done) {
+int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
+                const uint8_t* xq_prepacked) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
   if (dgrad_tf32 || !wgrad_shape_ok(H, W, Ci, k) || !tc_shape_ok(H, W, Co, Ci, k, 2)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out | (uintptr_t)gx) & 15) != 0) return CG_ERR_UNSUPPORTED;
+  if (xq_prepacked && !(Ci == 64 || Ci % 128 == 0)) return CG_ERR_UNSUPPORTED;
   GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g));
-  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done));
+  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done, xq_prepacked));
   // dgrad = forward convolution of gy (Co channels in) with the flipped weights (Ci channels out)
   return conv_tc_run<2>(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k, g.scale2, g.gq);
 }

@@ -170,13 +170,13 @@ static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H
   return conv_fwd(x, L.Wp, L.bp, y, N, H, W, L.s.Ci, L.s.Co, L.s.k);
 }
 // accumulates dW, db into the flat gradient; gx may be null
-static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W) {
+static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W, const uint8_t* xq = nullptr) {   // xq: cached operand for x
   cg_layer& L = m->layers[li];
   long M = (long)N * H * W;
   // plain convolutions let the engine add straight into the Torch-layout gradient; Linear layers beside an nn.View need the permuting unpack
   float* gW_direct = (L.s.in_hw == 1 && L.s.out_hw == 1) ? m->G + L.oW : nullptr;
   int direct = 0;
-  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
+  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct, xq));
   else CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
   if (!direct) CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
   if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
@@ -188,6 +188,14 @@ static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float
 }
 
 // =================================================================== G
+// A stage whose input can be produced straight into the tensor-core operand: PReLU(BN(.)) -> upsample -> fp16 pack in one pass
+// (conv_tc.cu: bn_prelu_up_pack); forward and weight gradient then share that buffer and no fp32 copy of the input exists.
+static bool g_stage_fused(const cg_model* g, int i, int h_in) {
+  if (i >= g->nst || ctx().conv_engine != 1 || !g->training) return false;
+  const cg_gstage& s = g->st[i]; int H = s.up ? 2 * h_in : h_in;
+  return conv_tc_cached_ok(H, H, s.Ci, s.Co, s.k);
+}
+
 int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
   CG_TRY(model_repack(g));
   g->nfw = 0; g->B = B;
@@ -195,36 +203,66 @@ int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
   float* zc = FW(g, (size_t)B * g->nz); NN(zc);
   CG_CUDA(cudaMemcpyAsync(zc, z_dev, sizeof(float) * (size_t)B * g->nz, cudaMemcpyDeviceToDevice, ctx().stream));
   g->z = zc;
-  g->lin = FW(g, B * F0); g->act0 = FW(g, B * F0); NN(g->lin); NN(g->act0);
+  g->lin = FW(g, B * F0); NN(g->lin);
   CG_TRY(layer_fwd(g, g->lin_layer, zc, g->lin, B, 1, 1));            // nn.Linear(nz, C0*s0*s0); output already NHWC
-  CG_TRY(prelu_fwd(g->lin, g->P + g->oLpw, g->act0, B * F0));
-  const float* cur = g->act0; int h = g->s0; long r = 0;
+  int h = g->s0; long r = 0;
+  bool fuse = g_stage_fused(g, 0, h);
+  const float* cur = nullptr;          // fp32 input of the next stage (unfused path)
+  const float* src = g->lin; int src_bn = -1;   // fused path: the tensor whose (BN +) PReLU is the next stage's input
+  if (!fuse) { g->act0 = FW(g, B * F0); NN(g->act0); CG_TRY(prelu_fwd(g->lin, g->P + g->oLpw, g->act0, B * F0)); cur = g->act0; }
   for (int i = 0; i < g->nst; ++i) {
     cg_gstage& s = g->st[i];
-    if (s.up) {
-      g->sup[i] = FW(g, (size_t)B * 4 * h * h * s.Ci); NN(g->sup[i]);
-      CG_TRY(upsample2x_fwd(cur, g->sup[i], B, h, h, s.Ci));
-      h *= 2; cur = g->sup[i];
-    } else g->sup[i] = (float*)cur;
+    const int hin = h; if (s.up) h *= 2;
     long M = (long)B * h * h, no = M * s.Co;
     g->sconv[i] = FW(g, no); NN(g->sconv[i]);
-    CG_TRY(layer_fwd(g, s.layer, cur, g->sconv[i], B, h, h));
-    g->sact[i] = FW(g, no); NN(g->sact[i]);
+    g->sfused[i] = fuse; g->sxq[i] = nullptr; g->sup[i] = nullptr;
+    if (fuse) {
+      uint8_t* xq = (uint8_t*)FW(g, conv_tc_operand_bytes(B, h, h, s.Ci, s.k) / 4); NN(xq);
+      float* bn_out = nullptr; const float *ga = nullptr, *be = nullptr, *me = nullptr, *iv = nullptr, *pw = g->P + g->oLpw;
+      if (src_bn >= 0) {
+        cg_gstage& q = g->st[src_bn];
+        bn_out = g->sbn[src_bn] = FW(g, (size_t)B * hin * hin * s.Ci); NN(bn_out);
+        ga = g->P + q.og; be = g->P + q.obt; me = g->smean[src_bn]; iv = g->sinv[src_bn]; pw = g->P + q.opw;
+      }
+      CG_TRY(bn_prelu_up_pack(src, ga, be, me, iv, pw, bn_out, xq, B, hin, hin, s.Ci, s.up, s.k));
+      g->sxq[i] = xq;
+      cg_layer& L = g->layers[s.layer];
+      CG_TRY(conv_fwd_tc_packed(xq, L.Wp, L.bp, g->sconv[i], B, h, h, s.Ci, s.Co, s.k));
+    } else {
+      if (s.up) {
+        g->sup[i] = FW(g, (size_t)M * s.Ci); NN(g->sup[i]);
+        CG_TRY(upsample2x_fwd(cur, g->sup[i], B, hin, hin, s.Ci));
+        cur = g->sup[i];
+      } else g->sup[i] = (float*)cur;
+      CG_TRY(layer_fwd(g, s.layer, cur, g->sconv[i], B, h, h));
+    }
+    const bool fuse_next = s.bn && g_stage_fused(g, i + 1, h);
+    g->sact[i] = nullptr; g->sbn[i] = nullptr;
     if (s.bn) {
-      g->sbn[i] = FW(g, no); g->smean[i] = FW(g, s.Co); g->sinv[i] = FW(g, s.Co); NN(g->sbn[i]); NN(g->smean[i]); NN(g->sinv[i]);
-      if (g->training)   // adversarial.train never switches G to evaluate(): batch statistics
-        CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
-      else
-        CG_TRY(bn_fwd_eval(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f));
+      g->smean[i] = FW(g, s.Co); g->sinv[i] = FW(g, s.Co); NN(g->smean[i]); NN(g->sinv[i]);
+      if (fuse_next) {   // statistics only; the next stage's producer applies them (g_stage_fused implies training mode)
+        CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, nullptr, g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
+        src = g->sconv[i]; src_bn = i;
+      } else {
+        g->sbn[i] = FW(g, no); g->sact[i] = FW(g, no); NN(g->sbn[i]); NN(g->sact[i]);
+        if (g->training)   // adversarial.train never switches G to evaluate(): batch statistics
+          CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
+        else
+          CG_TRY(bn_fwd_eval(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f));
+        CG_TRY(prelu_fwd(g->sbn[i], g->P + s.opw, g->sact[i], no));
+        cur = g->sact[i];
+      }
       r += 2 * s.Co;
-      CG_TRY(prelu_fwd(g->sbn[i], g->P + s.opw, g->sact[i], no));
-    } else CG_TRY(sigmoid_fwd(g->sconv[i], g->sact[i], no));
-    cur = g->sact[i];
+    } else {
+      g->sact[i] = FW(g, no); NN(g->sact[i]);
+      CG_TRY(sigmoid_fwd(g->sconv[i], g->sact[i], no));
+      cur = g->sact[i];
+    }
+    fuse = fuse_next;
   }
   CG_TRY(nhwc_to_nchw(cur, out_nchw, B, g->C, 32 * 32));
   return CG_OK;
 }
-
 int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
   if (!g->B) return set_err(CG_ERR_STATE, "G backward before forward");
   if (!g->training) return set_err(CG_ERR_STATE, "G backward needs a training-mode forward (batch-stat BN)");
@@ -241,7 +279,7 @@ int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
       CG_TRY(bn_bwd(g->sconv[i], gbn, g->P + s.og, g->smean[i], g->sinv[i], gconv, g->G + s.og, g->G + s.obt, M, s.Co));
     } else CG_TRY(sigmoid_bwd(g->sact[i], gcur, gconv, no));
     float* gin = BW(g, (size_t)M * s.Ci); NN(gin);
-    CG_TRY(layer_bwd(g, s.layer, g->sup[i], gconv, gin, B, h, h));
+    CG_TRY(layer_bwd(g, s.layer, g->sup[i], gconv, gin, B, h, h, g->sfused[i] ? g->sxq[i] : nullptr));
     if (s.up) {
       h /= 2;
       float* gs = BW(g, (size_t)B * h * h * s.Ci); NN(gs);

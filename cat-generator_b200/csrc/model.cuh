@@ -40,6 +40,7 @@ struct cg_model {
   float* run = nullptr; long nrun = 0;
   const float* z = nullptr; float *lin = nullptr, *act0 = nullptr;
   float *sup[4], *sconv[4], *sbn[4], *sact[4], *smean[4], *sinv[4];
+  const uint8_t* sxq[4]; bool sfused[4];      // stage input cached as the tensor-core operand (then sup[i] is null)
   // ---- D
   cg_stn stn[4];
   int t1, t2, b1[4], b2[4], h1, h2;          // layer indices

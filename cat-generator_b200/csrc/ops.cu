@@ -292,7 +292,7 @@ int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y
   CG_LAUNCH(k_colreduce<0>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
   CG_LAUNCH(k_bn_stats_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, eps, mom, mean, invstd, run_mean, run_var);
   long n = M * C;
-  CG_LAUNCH(k_bn_apply, grid1d(n, 256, 4), 256, 0, x, gamma, beta, mean, invstd, y, n, C);
+  if (y) CG_LAUNCH(k_bn_apply, grid1d(n, 256, 4), 256, 0, x, gamma, beta, mean, invstd, y, n, C);   // y == nullptr: statistics only (the caller fuses the apply)
   return CG_OK;
 }
 __global__ void k_bn_eval(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,

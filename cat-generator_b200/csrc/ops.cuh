@@ -77,6 +77,13 @@ int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W,
 int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr);
 int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk);
 // both gradients of one layer (gWp_out overwritten, gx written)
-int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr);
+int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr,
+                  const uint8_t* xq = nullptr);
+// cached fp16 operand path of the tensor-core engine (conv_tc.cu): PReLU(BN(x)) -> 2x upsample -> packed operand in one pass
+bool conv_tc_cached_ok(int H, int W, int Ci, int Co, int k);
+size_t conv_tc_operand_bytes(int N, int H, int W, int Ci, int k);
+int bn_prelu_up_pack(const float* x, const float* gamma, const float* beta, const float* mean, const float* invstd, const float* pw,
+                     float* bn_out, uint8_t* xq, int N, int h, int w, int C, int up, int k);
+int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 
 }  // namespace cg

@@ -61,6 +61,45 @@ void* workspace(size_t bytes) { return grow(&ctx().ws, &ctx().ws_bytes, bytes); 
 void* workspace2(size_t bytes) { return grow(&ctx().ws2, &ctx().ws2_bytes, bytes); }
 void* workspace3(size_t bytes) { return grow(&ctx().ws3, &ctx().ws3_bytes, bytes); }
 void* workspace4(size_t bytes) { return grow(&ctx().ws4, &ctx().ws4_bytes, bytes); }
+int lanes_fork() {
+  Ctx& c = ctx();
+  if (!c.lanes_on) return CG_OK;
+  if (c.lane != -1) return set_err(CG_ERR_STATE, "lanes_fork inside a lane");
+  if (!c.fork_ev) {
+    CG_CUDA(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
+    for (auto& L : c.lanes) { CG_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)); CG_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
+  }
+  CG_CUDA(cudaEventRecord(c.fork_ev, c.stream));
+  for (auto& L : c.lanes) CG_CUDA(cudaStreamWaitEvent(L.stream, c.fork_ev, 0));
+  return CG_OK;
+}
+int lane_enter(int b) {
+  Ctx& c = ctx();
+  if (!c.lanes_on) return CG_OK;
+  if (c.lane != -1 || b < 0 || b >= Ctx::kLanes || !c.fork_ev) return set_err(CG_ERR_STATE, "lane_enter(%d) in lane %d", b, c.lane);
+  Ctx::Lane& L = c.lanes[b];
+  c.saved.stream = c.stream; c.saved.ws = c.ws; c.saved.ws_bytes = c.ws_bytes; c.saved.ws3 = c.ws3; c.saved.ws3_bytes = c.ws3_bytes; c.saved.ws4 = c.ws4; c.saved.ws4_bytes = c.ws4_bytes;
+  c.stream = L.stream; c.ws = L.ws; c.ws_bytes = L.ws_bytes; c.ws3 = L.ws3; c.ws3_bytes = L.ws3_bytes; c.ws4 = L.ws4; c.ws4_bytes = L.ws4_bytes;
+  c.lane = b;
+  return CG_OK;
+}
+int lane_exit() {
+  Ctx& c = ctx();
+  if (!c.lanes_on) return CG_OK;
+  if (c.lane < 0) return set_err(CG_ERR_STATE, "lane_exit outside a lane");
+  Ctx::Lane& L = c.lanes[c.lane];
+  L.ws = c.ws; L.ws_bytes = c.ws_bytes; L.ws3 = c.ws3; L.ws3_bytes = c.ws3_bytes; L.ws4 = c.ws4; L.ws4_bytes = c.ws4_bytes;   // scratch may have grown
+  c.stream = c.saved.stream; c.ws = c.saved.ws; c.ws_bytes = c.saved.ws_bytes; c.ws3 = c.saved.ws3; c.ws3_bytes = c.saved.ws3_bytes; c.ws4 = c.saved.ws4; c.ws4_bytes = c.saved.ws4_bytes;
+  c.lane = -1;
+  return CG_OK;
+}
+int lanes_join() {
+  Ctx& c = ctx();
+  if (!c.lanes_on) return CG_OK;
+  if (c.lane != -1) return set_err(CG_ERR_STATE, "lanes_join inside a lane");
+  for (auto& L : c.lanes) { CG_CUDA(cudaEventRecord(L.done, L.stream)); CG_CUDA(cudaStreamWaitEvent(c.stream, L.done, 0)); }
+  return CG_OK;
+}
 void* pinned(size_t bytes) {
   Ctx& c = ctx();
   if (c.pinned_bytes >= bytes && c.pinned) return c.pinned;
@@ -117,6 +156,7 @@ int cg_init(int device) {
   if (p.major != 10) return set_err(CG_ERR_NODEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
   c.sm_count = p.multiProcessorCount;
   CG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  { const char* e = getenv("CATGEN_LANES"); c.lanes_on = !(e && e[0] == '0'); }
   c.device = device; c.inited = true; c.launches = 0;
   return CG_OK;
 }
@@ -129,6 +169,13 @@ void cg_shutdown(void) {
 #endif
   if (c.ws) cudaFree(c.ws); if (c.ws2) cudaFree(c.ws2); if (c.ws3) cudaFree(c.ws3); if (c.ws4) cudaFree(c.ws4); if (c.pinned) cudaFreeHost(c.pinned);
   c.ws = c.ws2 = c.ws3 = c.ws4 = c.pinned = nullptr; c.ws_bytes = c.ws2_bytes = c.ws3_bytes = c.ws4_bytes = c.pinned_bytes = 0;
+  for (auto& L : c.lanes) {
+    if (L.ws) cudaFree(L.ws); if (L.ws3) cudaFree(L.ws3); if (L.ws4) cudaFree(L.ws4);
+    if (L.stream) cudaStreamDestroy(L.stream); if (L.done) cudaEventDestroy(L.done);
+    L = Ctx::Lane();
+  }
+  if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
+  c.lane = -1;
   cudaStreamDestroy(c.stream); c.stream = nullptr; c.inited = false; c.device = -1; c.world = 1; c.rank = 0;
 }
 const char* cg_last_error(void) { return ctx().err; }
@@ -188,6 +235,8 @@ int cg_model_create(cg_model** out, int kind, int C, int nz, uint64_t seed) {
 int cg_model_free(cg_model* m) {
   if (!m) return CG_OK;
   cudaStreamSynchronize(ctx().stream);
+  for (auto& L : m->layers) { cg::conv_tc_unregister_wslices(L.Wp); cg::conv_tc_unregister_wslices(L.Wd); }
+  if (m->wq) cudaFree(m->wq); if (m->jobs_dev) cudaFree(m->jobs_dev);
   if (m->P) cudaFree(m->P); if (m->G) cudaFree(m->G); if (m->packed) cudaFree(m->packed); if (m->run) cudaFree(m->run);
   if (m->masks) cudaFree(m->masks); if (m->mq) cudaFree(m->mq); if (m->rng_dev) cudaFree(m->rng_dev);
   for (auto& b : m->fw) b.release(); for (auto& b : m->bw) b.release(); m->gwp.release();

@@ -27,6 +27,15 @@ struct Ctx {
   void* ws3 = nullptr; size_t ws3_bytes = 0;
   void* ws4 = nullptr; size_t ws4_bytes = 0;
   void* pinned = nullptr; size_t pinned_bytes = 0;
+  // lanes: independent branches of one model (D32_st3's four transformer branches) issue on their own stream with their own
+  // scratch, forked from / joined to `stream` by events -- which CUDA-graph capture records as parallel paths.  lane_enter()
+  // swaps `stream`, ws, ws3, ws4 with the lane's, so every launcher keeps using ctx().stream / workspace*() unchanged.
+  struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; void *ws = nullptr, *ws3 = nullptr, *ws4 = nullptr; size_t ws_bytes = 0, ws3_bytes = 0, ws4_bytes = 0; };
+  static constexpr int kLanes = 4;
+  Lane lanes[kLanes], saved;
+  int lane = -1;                // -1: the main stream
+  int lanes_on = 1;             // CATGEN_LANES=0 serialises the branches on the main stream
+  cudaEvent_t fork_ev = nullptr;
   // data parallel
   int rank = 0, world = 1;
   void* nccl = nullptr;
@@ -48,6 +57,10 @@ void* workspace3(size_t bytes);   // device scratch #3: tensor-core operand pack
                                   // reallocates, and ws2 pointers are live across the whole forward/backward call)
 void* workspace4(size_t bytes);   // device scratch #4: the packed gradient operand shared by dgrad and wgrad of one layer (outlives both runs' ws3 use)
 void* pinned(size_t bytes);       // pinned host staging
+int lanes_fork();                 // lanes may start after everything issued on the main stream so far
+int lane_enter(int b);            // route launches + scratch to lane b (no-op when lanes are off)
+int lane_exit();
+int lanes_join();                 // the main stream waits for every lane
 
 #define CG_CUDA(expr)                                                                         \
   do {                                                                                        \

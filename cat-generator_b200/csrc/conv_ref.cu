@@ -7,13 +7,6 @@
 namespace cg {
 
 // ------------------------------------------------------------------ parameter packing
-__device__ __forceinline__ long torch_index(int k, int Ci, int Co, int in_hw, int out_hw, int ky, int kx, int cip, int cop) {
-  if (in_hw == 1 && out_hw == 1) return (((long)cop * Ci + cip) * k + ky) * k + kx;          // conv, or plain Linear
-  int Civ = Ci / in_hw, Cov = Co / out_hw;                                                      // Linear beside an nn.View
-  int fi = (cip % Civ) * in_hw + cip / Civ;
-  int fo = (cop % Cov) * out_hw + cop / Cov;
-  return (long)fo * Ci + fi;
-}
 __global__ void k_pack_fprop(const float* __restrict__ W, float* __restrict__ Wp, long n, ConvSpec s) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
@@ -306,7 +299,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
 int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done);
 int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
-                const uint8_t* xq_prepacked);
+                const uint8_t* xq_prepacked, float* gb_acc, int* bias_done);
 void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valued inputs (tools/backward_precision_study.py)
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
@@ -330,9 +323,10 @@ int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, in
 // weight gradient + input gradient of one layer; the tensor-core engine packs the gradient operand once for both
 // xq (optional): the forward's cached fp16 operand for x; then x may be null and only the tensor-core engine can serve the call
 int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
-                  const uint8_t* xq) {
+                  const uint8_t* xq, float* gb_acc, int* bias_done) {
   if (done) *done = 0;
-  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k, gW_acc, done, xq); if (s != CG_ERR_UNSUPPORTED) return s; }
+  if (bias_done) *bias_done = 0;
+  if (ctx().conv_engine == 1) { int s = conv_bwd_tc(x, gy, Wd, gWp_out, gx, N, H, W, Ci, Co, k, gW_acc, done, xq, gb_acc, bias_done); if (s != CG_ERR_UNSUPPORTED) return s; }
   if (!x) return set_err(CG_ERR_STATE, "this forward cached only the tensor-core operand of the layer input; backward needs the same conv engine");
   CG_TRY(conv_wgrad(x, gy, gWp_out, N, H, W, Ci, Co, k, gW_acc, done));
   return conv_dgrad(gy, Wd, gx, N, H, W, Ci, Co, k);

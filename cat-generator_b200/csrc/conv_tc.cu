@@ -16,6 +16,7 @@
 //    tools/backward_precision_study.py: bf16 and unscaled fp16 gradients miss the parity targets.
 // Warp roles (160 threads): warp 4 = weight-slice producer (1 lane) ; warp 5? no -- see kernel: warps 0-3 are
 // the epilogue (they own the four TMEM lane quarters), warp 4 streams weights, warp 5 loads patches, warp 6 issues MMAs.
+#include <unordered_map>
 #include "ops.cuh"
 #include <cuda.h>
 #include <stdlib.h>   // CUtensorMap types only; the encoder is resolved through the runtime (no -lcuda)
@@ -198,6 +199,56 @@ __global__ void k_pack_wslices(const float* __restrict__ Wp, uint8_t* __restrict
     }
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
+}
+
+// Whole-model repack: a flat grid, each layer owning a run of blocks proportional to its weight count; phases run over disjoint outputs so no ordering is needed inside the launch.
+// The fp16 slices are gathered straight from the Torch-layout weight (same values as k_pack_wslices<2> applied to Wp / Wd).
+__device__ __forceinline__ void pack_slices_job(const float* __restrict__ W, uint8_t* __restrict__ Wq, const ConvSpec& s, int dgrad, int CB, long tid, long nthreads) {
+  const int k = s.k, kk = k * k;
+  const int Cin = dgrad ? s.Co : s.Ci, Cout = dgrad ? s.Ci : s.Co;         // the forward conv this operand feeds: Cin -> Cout
+  const int Cip = ((Cin + 63) / 64) * 64, Cop = ((Cout + 15) / 16) * 16, nsub = CB / 64;
+  const long nchunks = (long)kk * Cip * Cop / 8;
+  for (long i = tid; i < nchunks; i += nthreads) {
+    int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 8); t /= 8; int sub = (int)(t % nsub); t /= nsub; int tap = (int)(t % kk); int cb = (int)(t / kk);
+    int ci0 = cb * CB + sub * 64 + c * 8;
+    int ky = tap / k, kx = tap % k; if (dgrad) { ky = k - 1 - ky; kx = k - 1 - kx; }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ci = ci0 + j;
+      v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, 1, 1, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
+    }
+    uint4 out; uint32_t* o = &out.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); o[j] = *reinterpret_cast<uint32_t*>(&h); }
+    reinterpret_cast<uint4*>(Wq)[i] = out;
+  }
+}
+__global__ void k_repack_model(const PackJob* __restrict__ jobs, int njobs) {
+  int j = 0;
+  while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].blk0) ++j;
+  const PackJob J = jobs[j];
+  const ConvSpec s = J.s;
+  const long tid = (blockIdx.x - J.blk0) * (long)blockDim.x + threadIdx.x, nth = (long)J.nblk * blockDim.x;
+  const long n = (long)s.k * s.k * s.Ci * s.Co;
+  for (long i = tid; i < n; i += nth) {     // Wp[(ky,kx,ci)][co]
+    int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
+    J.Wp[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)];
+  }
+  if (J.need_dgrad) for (long i = tid; i < n; i += nth) {     // Wd[(ky,kx,co)][ci], taps flipped
+    int ci = (int)(i % s.Ci); long r = i / s.Ci; int co = (int)(r % s.Co); int tap = (int)(r / s.Co);
+    J.Wd[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, s.k - 1 - tap / s.k, s.k - 1 - tap % s.k, ci, co)];
+  }
+  for (long cop = tid; cop < s.Co; cop += nth) {
+    int Cov = s.Co / s.out_hw;
+    J.bp[cop] = J.b[s.out_hw == 1 ? (int)cop : (int)(cop % Cov) * s.out_hw + (int)(cop / Cov)];
+  }
+  if (J.wqf) pack_slices_job(J.W, J.wqf, s, 0, J.CBf, tid, nth);
+  if (J.wqd) pack_slices_job(J.W, J.wqd, s, 1, J.CBd, tid, nth);
+}
+int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks) {
+  CG_LAUNCH(k_repack_model, total_blocks, 256, 0, jobs_dev, njobs);
+  return CG_OK;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -388,6 +439,39 @@ static bool tc_shape_ok(int H, int W, int Ci, int Co, int k, int ES) {
   return (k == 3 || k == 5 || k == 7) && W % 8 == 0 && H % 8 == 0;
 }
 
+// Tile plan of the forward-conv kernel for padded Ci -> Co channels (shared with the model-level weight packer).
+//   NB: columns per CTA = largest multiple of 16 that divides Co and is <= 256
+//   TL: tiles per CTA -- prefer TWO tiles sharing each weight slice (halves the L2->SM weight stream per MMA)
+//   CB: the largest channel block that keeps 2 x TL patch buffers + a >= 4-deep weight ring (>= 3 for TL = 1) inside ~212 KB
+template <int ES>
+static void tc_plan(int Ci, int Co, int k, int ntiles, int* NBo, int* TLo, int* CBo) {
+  constexpr int PER = 16 / ES, KB = 128 / ES;
+  const int p = (k - 1) / 2, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
+  int NB = Co; while (NB > 256 || Co % NB) NB -= 16;
+  size_t slice_bytes = (size_t)(KB / PER) * NB * 16;
+  int TL = 1, CB = 0;
+  for (int tl = (ntiles >= 2 && 2 * NB <= 512) ? 2 : 1; tl >= 1 && !CB; --tl)
+    for (int cand = Ci; cand >= KB; cand -= KB) {
+      if (Ci % cand) continue;
+      size_t pb = (size_t)(cand / PER) * Hp * Wpx * 16;
+      if (2 * tl * pb + (size_t)(tl == 2 ? 4 : 3) * slice_bytes <= 212 * 1024) { CB = cand; TL = tl; break; }
+    }
+  *NBo = NB; *TLo = TL; *CBo = CB;
+}
+
+// fp16 weight slices packed once per parameter update by repack_model(), keyed by the fp32 operand pointer the caller passes
+struct WSliceEntry { const uint8_t* wq; int CB; };
+static std::unordered_map<const float*, WSliceEntry>& wslice_registry() { static std::unordered_map<const float*, WSliceEntry> r; return r; }
+void conv_tc_register_wslices(const float* key, const uint8_t* wq, int CB) { wslice_registry()[key] = WSliceEntry{wq, CB}; }
+void conv_tc_unregister_wslices(const float* key) { wslice_registry().erase(key); }
+bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
+  if (!(k == 3 || k == 5 || k == 7)) return false;
+  const int Ci = ((Cin + 63) / 64) * 64, Co = ((Cout + 15) / 16) * 16;
+  int NB, TL; tc_plan<2>(Ci, Co, k, 2, &NB, &TL, CB);
+  *bytes = (size_t)k * k * Ci * Co * 2;
+  return *CB != 0;
+}
+
 template <int ES>
 static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
                        const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
@@ -397,19 +481,10 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p;
   const int Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
   TcParams P{};
-  // N columns per CTA: largest multiple of 16 that divides Co and is <= 256
-  int NB = Co; while (NB > 256 || Co % NB) NB -= 16;
-  // tiles per CTA and channel block: prefer TWO tiles sharing each weight slice (halves the L2->SM weight stream per MMA), then
-  // the largest channel block that keeps 2 x TL patch buffers + a >= 4-deep weight ring (>= 3 for TL = 1) inside ~212 KB
+  int NB, TL, CB;
+  tc_plan<ES>(Ci, Co, k, N * (W / 8) * ((H + 15) / 16), &NB, &TL, &CB);
   size_t slice_bytes = (size_t)(KB / PER) * NB * 16;
   const int ntiles = N * (W / 8) * ((H + 15) / 16);
-  int TL = 1, CB = 0;
-  for (int tl = (ntiles >= 2 && 2 * NB <= 512) ? 2 : 1; tl >= 1 && !CB; --tl)
-    for (int cand = Ci; cand >= KB; cand -= KB) {
-      if (Ci % cand) continue;
-      size_t pb = (size_t)(cand / PER) * Hp * Wpx * 16;
-      if (2 * tl * pb + (size_t)(tl == 2 ? 4 : 3) * slice_bytes <= 212 * 1024) { CB = cand; TL = tl; break; }
-    }
   if (!CB) return CG_ERR_UNSUPPORTED;
   size_t patch_bytes = (size_t)(CB / PER) * Hp * Wpx * 16;
   int S = (int)((216 * 1024 - 2 * TL * patch_bytes) / slice_bytes); if (S > 8) S = 8;
@@ -417,13 +492,19 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   size_t smem = 2 * TL * patch_bytes + (size_t)S * slice_bytes;
   // operand buffers: activations then weight slices (16-byte aligned)
   size_t xq_bytes = (size_t)N * (Ci / PER) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * ES;
-  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : xq_bytes) + wq_bytes + 512);
+  const uint8_t* wq_cached = nullptr;
+  if (ES == 2) { auto it = wslice_registry().find(Wp); if (it != wslice_registry().end() && it->second.CB == CB) wq_cached = it->second.wq; }
+  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : xq_bytes) + (wq_cached ? 0 : wq_bytes) + 512);
   if (!ws) return CG_ERR_CUDA;
   const uint8_t* xq = xq_prepacked ? xq_prepacked : ws;
-  uint8_t* wq = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
+  const uint8_t* wq = wq_cached;
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
   if (!xq_prepacked) CG_LAUNCH(k_pack_act<ES>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2);
-  CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk, CB);
+  if (!wq_cached) {
+    uint8_t* wqb = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
+    CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wqb, nw, Cir, Cor, Co, kk, CB);
+    wq = wqb;
+  }
   P.xq = xq; P.wq = wq; P.bias = bias; P.y = y; P.scale2 = scale2;
   P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
   P.CB = CB; P.ncb = Ci / CB; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S; P.TL = TL; P.ntiles = ntiles;
@@ -452,26 +533,31 @@ void conv_tc_set_gradient_operands(int on) { g_tc_grad_operands = on; }
 __global__ void k_absmax(const float* __restrict__ x, long n, unsigned int* __restrict__ out);
 __global__ void k_make_scale(const unsigned int* __restrict__ amax, float* __restrict__ scale2);
 
-static float* tc_scale_scratch() {   // [scale, 1/scale, amax bits]: its own allocation, workspace3 may be regrown by the run
-  static float* p = nullptr;
-  if (!p && cudaMalloc(&p, 16 * sizeof(float)) != cudaSuccess) p = nullptr;
-  return p;
+static float* tc_scale_scratch() {   // per lane: [scale, 1/scale, amax bits, amax bits (fused path, kept zero between uses)]; its own allocation, workspace3 may be regrown by the run
+  static float* p[Ctx::kLanes + 1] = {nullptr};
+  float*& q = p[ctx().lane + 1];
+  if (!q) { if (cudaMalloc(&q, 16 * sizeof(float)) != cudaSuccess || cudaMemset(q, 0, 16 * sizeof(float)) != cudaSuccess) q = nullptr; }
+  return q;
 }
 
 // ONE packed gradient operand per layer: gq[N][Cg/8][Hq][Wq][8] fp16, zero-padded by the filter radius, channels padded to 64,
 // multiplied by the per-tensor power of two.  dgrad reads halo'd patches from it (A operand), wgrad reads 16x8-pixel tiles
 // from it (B operand) through a second tensor map.  Before this, gy was read three times per layer (absmax, tf32 pack, fp16 tile pack).
 struct GradOperand { const uint8_t* gq; const float* scale2; int Cg; };
-static int pack_grad_operand(const float* gy, int N, int H, int W, int C, int k, GradOperand* out) {
+// gb_acc (optional): also add the bias gradient (column sums of gy) -- it comes out of the same pass as max|gy|
+static int pack_grad_operand(const float* gy, int N, int H, int W, int C, int k, GradOperand* out, float* gb_acc = nullptr) {
   const int p = (k - 1) / 2, Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Cg = ((C + 63) / 64) * 64;
   float* sc = tc_scale_scratch(); if (!sc) return set_err(CG_ERR_CUDA, "scale scratch allocation failed");
   unsigned int* amax = (unsigned int*)(sc + 2);
   size_t bytes = (size_t)N * (Cg / 8) * Hq * Wq * 16;
   uint8_t* gq = (uint8_t*)workspace4(bytes + 256); if (!gq) return CG_ERR_CUDA;
-  CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
   long n = (long)N * H * W * C;
-  CG_LAUNCH(k_absmax, grid1d(n, 256, 8), 256, 0, gy, n, amax);
-  CG_LAUNCH(k_make_scale, 1, 1, 0, amax, sc);
+  if (gb_acc) CG_TRY(colsum_acc_absmax(gy, gb_acc, (long)N * H * W, C, amax + 1, sc));
+  else {
+    CG_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx().stream));
+    CG_LAUNCH(k_absmax, grid1d(n, 256, 8), 256, 0, gy, n, amax);
+    CG_LAUNCH(k_make_scale, 1, 1, 0, amax, sc);
+  }
   long nq = (long)(bytes / 16);
   CG_LAUNCH(k_pack_act<2>, grid1d(nq, 256), 256, 0, gy, gq, nq, H, W, C, Cg, p, Hq, Wq, (const float*)sc);
   out->gq = gq; out->scale2 = sc; out->Cg = Cg;
@@ -755,12 +841,13 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
 // Whole backward of one conv layer: weight gradient AND input gradient from ONE packed gradient operand.
 //   gWp_out[(tap,ci)][co] (overwritten) ; gx[N,H,W,Ci] = conv(gy, Wd)
 int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
-                const uint8_t* xq_prepacked) {
+                const uint8_t* xq_prepacked, float* gb_acc, int* bias_done) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
   if (dgrad_tf32 || !wgrad_shape_ok(H, W, Ci, k) || !tc_shape_ok(H, W, Co, Ci, k, 2)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gWp_out | (uintptr_t)gx) & 15) != 0) return CG_ERR_UNSUPPORTED;
   if (xq_prepacked && !(Ci == 64 || Ci % 128 == 0)) return CG_ERR_UNSUPPORTED;
-  GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g));
+  GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g, gb_acc));
+  if (gb_acc && bias_done) *bias_done = 1;
   CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done, xq_prepacked));
   // dgrad = forward convolution of gy (Co channels in) with the flipped weights (Ci channels out)
   return conv_tc_run<2>(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k, g.scale2, g.gq);

@@ -116,6 +116,29 @@ int model_build(cg_model* m) {
     if (nW > maxW) maxW = nW;
   }
   CG_TRY(m->gwp.ensure(maxW + 32768));
+  // one-launch repack: a job per layer, with fp16 weight slices for the layers/directions the tensor-core engine takes
+  {
+    std::vector<cg::PackJob> jobs(m->layers.size());
+    size_t wq_total = 0;
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+      cg_layer& L = m->layers[i]; cg::PackJob& J = jobs[i];
+      J.W = m->P + L.oW; J.b = m->P + L.ob; J.Wp = L.Wp; J.Wd = L.Wd; J.bp = L.bp; J.s = L.s; J.need_dgrad = L.need_dgrad ? 1 : 0;
+      J.wqf = J.wqd = nullptr; J.CBf = J.CBd = 0;
+      { long nW = (long)L.s.Co * L.s.Ci * L.s.k * L.s.k; J.blk0 = m->repack_blocks; J.nblk = (int)((nW + 2047) / 2048); m->repack_blocks += J.nblk; }
+      size_t bf = 0, bd = 0;
+      if (L.s.in_hw == 1 && L.s.out_hw == 1 && conv_tc_wslice_plan(L.s.Ci, L.s.Co, L.s.k, &J.CBf, &bf)) { J.wqf = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bf + 255) & ~(size_t)255; }
+      if (L.need_dgrad && L.s.in_hw == 1 && L.s.out_hw == 1 && conv_tc_wslice_plan(L.s.Co, L.s.Ci, L.s.k, &J.CBd, &bd)) { J.wqd = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bd + 255) & ~(size_t)255; }
+    }
+    if (wq_total) CG_CUDA(cudaMalloc(&m->wq, wq_total));
+    for (size_t i = 0; i < jobs.size(); ++i) {   // offsets (+1 so that offset 0 is distinguishable from "none") -> pointers
+      cg::PackJob& J = jobs[i];
+      if (J.wqf) { J.wqf = m->wq + ((uintptr_t)J.wqf - 1); conv_tc_register_wslices(J.Wp, J.wqf, J.CBf); }
+      if (J.wqd) { J.wqd = m->wq + ((uintptr_t)J.wqd - 1); conv_tc_register_wslices(J.Wd, J.wqd, J.CBd); }
+    }
+    m->njobs = (int)jobs.size();
+    CG_CUDA(cudaMalloc(&m->jobs_dev, sizeof(cg::PackJob) * jobs.size()));
+    CG_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), sizeof(cg::PackJob) * jobs.size(), cudaMemcpyHostToDevice));
+  }
   if (m->nrun) {
     CG_CUDA(cudaMalloc(&m->run, sizeof(float) * m->nrun));
     long r = 0;
@@ -155,16 +178,24 @@ int model_build(cg_model* m) {
 
 int model_repack(cg_model* m) {
   if (!m->dirty) return CG_OK;
-  for (auto& L : m->layers) {
-    CG_TRY(pack_fprop(m->P + L.oW, L.Wp, L.s));
-    if (L.need_dgrad) CG_TRY(pack_dgrad(m->P + L.oW, L.Wd, L.s));
-    CG_TRY(pack_bias(m->P + L.ob, L.bp, L.s));
-  }
+  CG_TRY(repack_model(m->jobs_dev, m->njobs, m->repack_blocks));   // every layer's fp32 operands + fp16 weight slices, one launch
   m->dirty = false;
   return CG_OK;
 }
 
 // x: [N,H,W,Ci] -> y: [N,H,W,Co]
+// wgrad scratch of the stream this call issues on (branches running in lanes must not share one)
+static float* gw_scratch(cg_model* m) {
+  int lane = ctx().lane;
+  if (lane < 0) return m->gwp.p;
+  if (m->gwp_lane[lane].ensure(m->gwp.n) != CG_OK) return nullptr;
+  return m->gwp_lane[lane].p;
+}
+struct LaneScope {   // routes the enclosed launches to lane b; leaves the lane on every exit path
+  int status; bool in;
+  explicit LaneScope(int b) : status(lane_enter(b)), in(status == CG_OK) {}
+  ~LaneScope() { if (in) lane_exit(); }
+};
 static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H, int W) {
   cg_layer& L = m->layers[li];
   return conv_fwd(x, L.Wp, L.bp, y, N, H, W, L.s.Ci, L.s.Co, L.s.k);
@@ -173,15 +204,18 @@ static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H
 static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W, const uint8_t* xq = nullptr) {   // xq: cached operand for x
   cg_layer& L = m->layers[li];
   long M = (long)N * H * W;
+  float* gwp = gw_scratch(m); NN(gwp);
   // plain convolutions let the engine add straight into the Torch-layout gradient; Linear layers beside an nn.View need the permuting unpack
   float* gW_direct = (L.s.in_hw == 1 && L.s.out_hw == 1) ? m->G + L.oW : nullptr;
   int direct = 0;
-  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, m->gwp.p, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct, xq));
-  else CG_TRY(conv_wgrad(x, gy, m->gwp.p, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
-  if (!direct) CG_TRY(unpack_wgrad_acc(m->gwp.p, m->G + L.oW, L.s));
-  if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
+  int bias_done = 0;
+  if (gx) CG_TRY(conv_backward(x, gy, L.Wd, gwp, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct, xq, L.s.out_hw == 1 ? m->G + L.ob : nullptr, &bias_done));
+  else CG_TRY(conv_wgrad(x, gy, gwp, N, H, W, L.s.Ci, L.s.Co, L.s.k, gW_direct, &direct));
+  if (!direct) CG_TRY(unpack_wgrad_acc(gwp, m->G + L.oW, L.s));
+  if (bias_done) {}   // the engine's single pass over gy produced it
+  else if (L.s.out_hw == 1) CG_TRY(colsum_acc(gy, m->G + L.ob, M, L.s.Co));
   else {
-    float* tmp = m->gwp.p;   // wgrad scratch is free again (stream ordered)
+    float* tmp = gwp;   // wgrad scratch is free again (stream ordered)
     CG_TRY(fill(tmp, 0.f, L.s.Co)); CG_TRY(colsum_acc(gy, tmp, M, L.s.Co)); CG_TRY(unpack_bias_acc(tmp, m->G + L.ob, L.s));
   }
   return CG_OK;
@@ -385,7 +419,10 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
   CG_TRY(avgpool2_fwd(d->ta2, d->tpool, B, 32, 32, 64));
   CG_TRY(mask_channels(d->tpool, mk, d->T, B, 256, 64)); mk += (long)B * 64;
   d->cat = FW(d, (size_t)B * 64 * 320); NN(d->cat);
+  // the four branches only read T and write disjoint channel ranges of cat: one lane each (models.lua:661-699, nn.Concat)
+  CG_TRY(lanes_fork());
   for (int b = 0; b < 4; ++b) {
+    LaneScope lane(b); CG_TRY(lane.status);
     int Co = b < 3 ? 64 : 128;
     const float* bin = d->T;
     if (b < 3) { CG_TRY(stn_forward(d, &d->stn[b + 1], d->T, B)); bin = d->stn[b + 1].out; }
@@ -401,6 +438,7 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
     CG_TRY(prelu_fwd(d->bc2[b], d->P + d->bpw2[b], tmp, n1 / 4));
     CG_TRY(copy_channels(tmp, d->cat, (long)B * 64, Co, 320, b * 64, 0));
   }
+  CG_TRY(lanes_join());
   d->catd = FW(d, (size_t)B * 20480); NN(d->catd);
   CG_TRY(mask_channels(d->cat, mk, d->catd, B, 64, 320)); mk += (long)B * 320;
   d->h1o = FW(d, (size_t)B * 256); d->ha1 = FW(d, (size_t)B * 256); d->hd = FW(d, (size_t)B * 256); NN(d->h1o); NN(d->ha1); NN(d->hd);
@@ -431,7 +469,10 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   long nT = (long)B * 256 * 64;
   float* gT = BW(d, nT); NN(gT); CG_TRY(fill(gT, 0.f, nT));
   const float* mk = mk_br;
+  const float* gT_part[4];      // each branch's gradient w.r.t. T, summed after the join in branch order (as nn.Concat does)
+  CG_TRY(lanes_fork());
   for (int b = 0; b < 4; ++b) {
+    LaneScope lane(b); CG_TRY(lane.status);
     int Co = b < 3 ? 64 : 128;
     long n2 = (long)B * 64 * Co, n1 = n2 * 4;
     float* go = BW(d, n2); NN(go); CG_TRY(copy_channels(gcat, go, (long)B * 64, Co, 320, b * 64, 1));
@@ -445,9 +486,11 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
     if (b < 3) {
       float* gs = BW(d, nT); NN(gs);
       CG_TRY(stn_backward(d, &d->stn[b + 1], gbin, gs, B));
-      CG_TRY(add_inplace(gT, gs, nT));
-    } else CG_TRY(add_inplace(gT, gbin, nT));
+      gT_part[b] = gs;
+    } else gT_part[b] = gbin;
   }
+  CG_TRY(lanes_join());
+  for (int b = 0; b < 4; ++b) CG_TRY(add_inplace(gT, gT_part[b], nT));
   float* gtp = BW(d, nT); NN(gtp); CG_TRY(mask_channels(gT, mk_trunk, gtp, B, 256, 64));
   long n64 = (long)B * 1024 * 64;
   float* gta2 = BW(d, n64); NN(gta2); CG_TRY(avgpool2_bwd(gtp, gta2, B, 32, 32, 64));

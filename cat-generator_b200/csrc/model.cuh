@@ -27,12 +27,14 @@ struct cg_model {
   float *P = nullptr, *G = nullptr;        // flat params / grads (device)
   std::vector<cg_layer> layers;
   float* packed = nullptr; size_t packed_floats = 0;
+  uint8_t* wq = nullptr; cg::PackJob* jobs_dev = nullptr; int njobs = 0, repack_blocks = 0;   // fp16 weight slices + the one-launch repack table
   bool dirty = true;                        // packed operands stale w.r.t. P
   int training = 1;
   uint64_t seed = 0, rng_offset = 0;          // rng_offset: host counter used only while initialising parameters
   unsigned long long* rng_dev = nullptr;      // Philox offset of the dropout masks, in device memory (graph replay)
   std::vector<cg::DBuf> fw, bw; int nfw = 0, nbw = 0;
-  cg::DBuf gwp;                              // packed wgrad scratch
+  cg::DBuf gwp;                              // packed wgrad scratch (main stream)
+  cg::DBuf gwp_lane[cg::Ctx::kLanes];        // ... and one per lane (concurrent branches)
   int B = 0;
   // ---- G
   int C0 = 0, s0 = 0, nst = 0; cg_gstage st[4];

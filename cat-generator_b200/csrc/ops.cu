@@ -357,6 +357,62 @@ int colsum_acc(const float* x, float* out_acc, long M, int C) {
   return CG_OK;
 }
 
+// colsum_acc fused with the tensor-core engine's gradient-operand statistics: one pass over gy yields the bias gradient
+// (same partials, same order as colsum_acc) AND max|gy|; the finalize kernel turns the maximum into the power-of-two scale
+// [scale, 1/scale] the fp16 gradient operand is packed with (conv_tc.cu) and re-zeroes the maximum for the next layer.
+__global__ void k_colreduce_absmax(const float* __restrict__ x, double* __restrict__ part, long M, int C, long rows_per_split, unsigned int* __restrict__ amax) {
+  __shared__ double sh[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long r0 = (long)blockIdx.y * rows_per_split, r1 = r0 + rows_per_split; if (r1 > M) r1 = M;
+  double a0 = 0; float mx = 0.f;
+  if (c < C) {
+    float f0 = 0; int cnt = 0;
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v = x[r * C + c];
+      f0 += v; mx = fmaxf(mx, fabsf(v));
+      if (++cnt == 64) { a0 += f0; f0 = 0; cnt = 0; }
+    }
+    a0 += f0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (threadIdx.x == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));   // non-negative floats order like uints
+  sh[threadIdx.y][threadIdx.x] = a0;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double s0 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s0 += sh[i][threadIdx.x];
+    part[((long)blockIdx.y * C + c) * 2 + 0] = s0;
+    part[((long)blockIdx.y * C + c) * 2 + 1] = 0.0;
+  }
+}
+__global__ void k_colsum_final_scale(const double* __restrict__ part, int S, int C, float* __restrict__ out_acc, unsigned int* __restrict__ amax, float* __restrict__ scale2) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float m = __uint_as_float(*amax);
+    float sc = 1.f;
+    if (m > 0.f && isfinite(m)) sc = exp2f(floorf(log2f(16384.f / m)));
+    if (!(sc > 0.f) || !isfinite(sc)) sc = 1.f;
+    scale2[0] = sc; scale2[1] = 1.f / sc;
+    *amax = 0u;
+  }
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s0, s1; col_partials(part, S, C, c, lane, s0, s1);
+  if (lane) return;
+  out_acc[c] += (float)s0;
+}
+int colsum_acc_absmax(const float* x, float* out_acc, long M, int C, unsigned int* amax_zeroed, float* scale2) {
+  int S = colreduce_splits(M, C);
+  long rps = (M + S - 1) / S;
+  double* part = (double*)workspace(sizeof(double) * 2 * (size_t)S * C);
+  if (!part) return CG_ERR_CUDA;
+  dim3 g(cdiv(C, 32), S), b(32, 8);
+  CG_LAUNCH(k_colreduce_absmax, g, b, 0, x, part, M, C, rps, amax_zeroed);
+  CG_LAUNCH(k_colsum_final_scale, cdiv(C, 4), 128, 0, part, S, C, out_acc, amax_zeroed, scale2);
+  return CG_OK;
+}
+
 // =================================================================== spatial transformer (A.11, [upstream] stn)
 // nn.AffineTransformMatrixGenerator: I * R(alpha) * S(s) * T(tx,ty), first two rows; R = [[c,-s],[s,c]]
 __device__ __forceinline__ void mat3mul(const float* a, const float* b, float* c) {

@@ -37,6 +37,8 @@ int bn_fwd_eval(const float* x, const float* gamma, const float* beta, float* y,
 int bn_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* invstd,
            float* gx, float* ggamma_acc, float* gbeta_acc, long M, int C);
 int colsum_acc(const float* x, float* out_acc, long M, int C);   // out[c] += sum_rows x[r,c]
+// same, plus max|x| -> the power-of-two operand scale [s, 1/s]; *amax_zeroed must be 0 on entry and is 0 again on exit
+int colsum_acc_absmax(const float* x, float* out_acc, long M, int C, unsigned int* amax_zeroed, float* scale2);
 
 // ---- spatial transformer
 int affine_matrix_fwd(const float* theta, float* A, int B, int rot, int scl, int trn);
@@ -63,6 +65,14 @@ struct ConvSpec {     // also describes nn.Linear as a 1x1 conv on a [N,1,1,in] 
   // Linear only: the Torch in/out feature index f = c*HW + s is permuted to the NHWC index s*C + c
   int in_hw = 1, out_hw = 1;
 };
+// index into the Torch-layout weight of (tap, input feature cip, output feature cop) in kernel (NHWC) order
+__device__ __forceinline__ long torch_index(int k, int Ci, int Co, int in_hw, int out_hw, int ky, int kx, int cip, int cop) {
+  if (in_hw == 1 && out_hw == 1) return (((long)cop * Ci + cip) * k + ky) * k + kx;          // conv, or plain Linear
+  int Civ = Ci / in_hw, Cov = Co / out_hw;                                                      // Linear beside an nn.View
+  int fi = (cip % Civ) * in_hw + cip / Civ;
+  int fo = (cop % Cov) * out_hw + cop / Cov;
+  return (long)fo * Ci + fi;
+}
 int pack_fprop(const float* W, float* Wp, const ConvSpec& s);    // Wp[(ky,kx,ci)][co]
 int pack_dgrad(const float* W, float* Wd, const ConvSpec& s);    // Wd[(ky,kx,co)][ci], taps flipped
 int pack_bias(const float* b, float* bp, const ConvSpec& s);     // permuted for Linear with out_hw > 1
@@ -78,12 +88,26 @@ int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, in
 int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk);
 // both gradients of one layer (gWp_out overwritten, gx written)
 int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr,
-                  const uint8_t* xq = nullptr);
+                  const uint8_t* xq = nullptr, float* gb_acc = nullptr, int* bias_done = nullptr);   // gb_acc: bias gradient; *bias_done = 1 when the engine added it
 // cached fp16 operand path of the tensor-core engine (conv_tc.cu): PReLU(BN(x)) -> 2x upsample -> packed operand in one pass
 bool conv_tc_cached_ok(int H, int W, int Ci, int Co, int k);
 size_t conv_tc_operand_bytes(int N, int H, int W, int Ci, int k);
 int bn_prelu_up_pack(const float* x, const float* gamma, const float* beta, const float* mean, const float* invstd, const float* pw,
                      float* bn_out, uint8_t* xq, int N, int h, int w, int C, int up, int k);
 int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
+
+
+// ---- whole-model repack in ONE launch (conv_tc.cu): fp32 fprop/dgrad/bias operands of every layer plus, for layers the
+// tensor-core engine takes, the fp16 weight slices of both directions.  The slices are registered under the fp32 operand's
+// pointer, so the engine finds them instead of re-packing per call.
+struct PackJob {
+  const float *W, *b; float *Wp, *Wd, *bp; uint8_t *wqf, *wqd;   // wqf/wqd null: not a tensor-core layer
+  ConvSpec s; int need_dgrad, CBf, CBd;
+  int blk0, nblk;                                                 // this job's slice of the flat grid (blocks proportional to its weight count)
+};
+int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks);
+bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes);   // fp16 forward-conv slices for Cin -> Cout
+void conv_tc_register_wslices(const float* key, const uint8_t* wq, int CB);
+void conv_tc_unregister_wslices(const float* key);
 
 }  // namespace cg

@@ -98,6 +98,46 @@ int lanes_join() {
   if (!c.lanes_on) return CG_OK;
   if (c.lane != -1) return set_err(CG_ERR_STATE, "lanes_join inside a lane");
   for (auto& L : c.lanes) { CG_CUDA(cudaEventRecord(L.done, L.stream)); CG_CUDA(cudaStreamWaitEvent(c.stream, L.done, 0)); }
+  for (int b = 1; b <= Ctx::kLanes; ++b) if (c.side[b].pending) { CG_CUDA(cudaStreamWaitEvent(c.stream, c.side[b].done, 0)); c.side[b].pending = false; }
+  return CG_OK;
+}
+int side_begin() {
+  Ctx& c = ctx();
+  if (!c.side_on || c.in_side) return 0;
+  Ctx::Side& W = c.side[c.lane + 1];
+  if (!W.stream) {
+    if (cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&W.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&W.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); W.stream = nullptr; return 0; }
+  }
+  if (cudaEventRecord(W.fork, c.stream) != cudaSuccess || cudaStreamWaitEvent(W.stream, W.fork, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  c.side_saved.stream = c.stream; c.side_saved.ws = c.ws; c.side_saved.ws_bytes = c.ws_bytes; c.side_saved.ws3 = c.ws3; c.side_saved.ws3_bytes = c.ws3_bytes;
+  c.stream = W.stream; c.ws = W.ws; c.ws_bytes = W.ws_bytes; c.ws3 = W.ws3; c.ws3_bytes = W.ws3_bytes;
+  c.in_side = true;
+  return 1;
+}
+int side_end() {
+  Ctx& c = ctx();
+  if (!c.in_side) return CG_OK;
+  Ctx::Side& W = c.side[c.lane + 1];
+  cudaError_t e = cudaEventRecord(W.done, W.stream);
+  W.pending = true;
+  W.ws = c.ws; W.ws_bytes = c.ws_bytes; W.ws3 = c.ws3; W.ws3_bytes = c.ws3_bytes;
+  c.stream = c.side_saved.stream; c.ws = c.side_saved.ws; c.ws_bytes = c.side_saved.ws_bytes; c.ws3 = c.side_saved.ws3; c.ws3_bytes = c.side_saved.ws3_bytes;
+  c.in_side = false;
+  if (e != cudaSuccess) return set_err(CG_ERR_CUDA, "side stream record failed: %s", cudaGetErrorString(e));
+  return CG_OK;
+}
+int side_wait() {
+  Ctx& c = ctx();
+  if (c.in_side) return set_err(CG_ERR_STATE, "side_wait on a side stream");
+  Ctx::Side& W = c.side[c.lane + 1];
+  if (W.pending) { CG_CUDA(cudaStreamWaitEvent(c.stream, W.done, 0)); W.pending = false; }
+  return CG_OK;
+}
+int side_wait_all() {
+  Ctx& c = ctx();
+  if (c.in_side || c.lane != -1) return set_err(CG_ERR_STATE, "side_wait_all outside the main stream");
+  for (auto& W : c.side) if (W.pending) { CG_CUDA(cudaStreamWaitEvent(c.stream, W.done, 0)); W.pending = false; }
   return CG_OK;
 }
 void* pinned(size_t bytes) {
@@ -157,6 +197,7 @@ int cg_init(int device) {
   c.sm_count = p.multiProcessorCount;
   CG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   { const char* e = getenv("CATGEN_LANES"); c.lanes_on = !(e && e[0] == '0'); }
+  { const char* e = getenv("CATGEN_SIDE"); c.side_on = !(e && e[0] == '0'); }
   c.device = device; c.inited = true; c.launches = 0;
   return CG_OK;
 }
@@ -175,6 +216,12 @@ void cg_shutdown(void) {
     L = Ctx::Lane();
   }
   if (c.fork_ev) { cudaEventDestroy(c.fork_ev); c.fork_ev = nullptr; }
+  for (auto& W : c.side) {
+    if (W.ws) cudaFree(W.ws); if (W.ws3) cudaFree(W.ws3);
+    if (W.stream) cudaStreamDestroy(W.stream); if (W.fork) cudaEventDestroy(W.fork); if (W.done) cudaEventDestroy(W.done);
+    W = Ctx::Side();
+  }
+  c.in_side = false;
   c.lane = -1;
   cudaStreamDestroy(c.stream); c.stream = nullptr; c.inited = false; c.device = -1; c.world = 1; c.rank = 0;
 }
@@ -220,6 +267,7 @@ int cg_set_graph_mode(int on) { ctx().graph_mode = on ? 1 : 0; return CG_OK; }
 int cg_get_graph_mode(void) { return ctx().graph_mode; }
 int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
 int cg_get_conv_engine(void) { return ctx().conv_engine; }
+int cg_set_dead_grad_elim(int on) { ctx().dead_grad_elim = on ? 1 : 0; return CG_OK; }
 
 // ------------------------------------------------------------------ models
 int cg_model_create(cg_model** out, int kind, int C, int nz, uint64_t seed) {
@@ -409,7 +457,13 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     CG_TRY(D_forward_dev(D, t->samples.p, B, nullptr, nullptr));   // t->dout keeps the last D-phase outputs for d_out
     float* dsig = D->hsig;
     CG_TRY(bce(dsig, tgtG, B, t->scal.p + si, t->df.p));
-    CG_TRY(D_backward_dev(D, t->df.p, t->gimg.p));   // also accumulates into D's grads, like the reference (zeroed by the next fevalD)
+    // The reference's MODEL_D:backward here also accumulates D's parameter gradients (adversarial.lua:193), which nothing reads:
+    // the next fevalD zeroes them (:78).  By default only the input-gradient path runs; cg_set_dead_grad_elim(0) restores the
+    // accumulation (then cg_model_get_grads(D) after a step returns what Torch's gradParameters would hold).
+    D->skip_param_grads = ctx().dead_grad_elim;
+    int bst = D_backward_dev(D, t->df.p, t->gimg.p);
+    D->skip_param_grads = 0;
+    CG_TRY(bst);
     CG_TRY(G_backward_dev(G, t->gimg.p, nullptr));
     CG_TRY(cg_dist_allreduce_grads(G));
     CG_TRY(penalty_clamp(G->G, G->P, G->np, c->G_L1, c->G_L2, c->G_L2, c->G_clamp, t->scal.p + si + 1));   // sign term uses G_L2 (adversarial.lua:206)
@@ -441,8 +495,8 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   bool eligible = X.graph_mode && !X.prof_on && !(t->D->mq && t->D->mq_next < t->D->mq_count);
   if (!eligible) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   cg_trainer::StepGraph* sg = nullptr;
-  for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg))) { sg = &e; break; }
-  if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; }
+  for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg)) && e.engine == X.conv_engine && e.elim == X.dead_grad_elim && e.lanes == X.lanes_on * 2 + X.side_on) { sg = &e; break; }
+  if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; sg->engine = X.conv_engine; sg->elim = X.dead_grad_elim; sg->lanes = X.lanes_on * 2 + X.side_on; }
   const int B = c->B, hB = B / 2; const size_t img = (size_t)t->G->C * 1024, nz = t->G->nz;
   const size_t nr = (size_t)c->d_iters * hB * img, nzd = (size_t)c->d_iters * hB * nz, nzg = (size_t)c->g_iters * B * nz;
   if (sg->failed || (!sg->exec && sg->warm < 2)) {

@@ -18,6 +18,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   int conv_engine = 1;
+  int dead_grad_elim = 1;       // cg_train_step: skip D's parameter gradients inside fevalG (zeroed unread by the next fevalD)
   int graph_mode = 1;           // replay the training step as a CUDA graph once warm (cg_set_graph_mode)
   int64_t launches = 0;
   char err[1024] = {0};
@@ -36,6 +37,12 @@ struct Ctx {
   int lane = -1;                // -1: the main stream
   int lanes_on = 1;             // CATGEN_LANES=0 serialises the branches on the main stream
   cudaEvent_t fork_ev = nullptr;
+  // side streams: one companion per stream above (index lane + 1).  A layer's weight-gradient chain is issued there while its
+  // input-gradient conv and the element-wise ops behind it continue on the owning stream (conv_tc.cu: conv_bwd_tc).
+  struct Side { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, done = nullptr; bool pending = false; void *ws = nullptr, *ws3 = nullptr; size_t ws_bytes = 0, ws3_bytes = 0; };
+  Side side[kLanes + 1], side_saved;
+  bool in_side = false;
+  int side_on = 1;              // CATGEN_SIDE=0 keeps the weight gradients on the owning stream
   // data parallel
   int rank = 0, world = 1;
   void* nccl = nullptr;
@@ -60,7 +67,11 @@ void* pinned(size_t bytes);       // pinned host staging
 int lanes_fork();                 // lanes may start after everything issued on the main stream so far
 int lane_enter(int b);            // route launches + scratch to lane b (no-op when lanes are off)
 int lane_exit();
-int lanes_join();                 // the main stream waits for every lane
+int lanes_join();                 // the main stream waits for every lane (and the lanes' side streams)
+int side_begin();                 // 1: launches now go to this stream's side stream (ordered after everything issued so far); 0: side streams off
+int side_end();                   // back to the owning stream; the side work is pending
+int side_wait();                  // the owning stream waits for its pending side work (before reusing what that work reads)
+int side_wait_all();              // main stream: every side stream's pending work
 
 #define CG_CUDA(expr)                                                                         \
   do {                                                                                        \

@@ -547,6 +547,7 @@ struct GradOperand { const uint8_t* gq; const float* scale2; int Cg; };
 // gb_acc (optional): also add the bias gradient (column sums of gy) -- it comes out of the same pass as max|gy|
 static int pack_grad_operand(const float* gy, int N, int H, int W, int C, int k, GradOperand* out, float* gb_acc = nullptr) {
   const int p = (k - 1) / 2, Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Cg = ((C + 63) / 64) * 64;
+  CG_TRY(side_wait());   // a weight-gradient chain on the side stream may still read the operand and scale rewritten below
   float* sc = tc_scale_scratch(); if (!sc) return set_err(CG_ERR_CUDA, "scale scratch allocation failed");
   unsigned int* amax = (unsigned int*)(sc + 2);
   size_t bytes = (size_t)N * (Cg / 8) * Hq * Wq * 16;
@@ -848,7 +849,19 @@ int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out
   if (xq_prepacked && !(Ci == 64 || Ci % 128 == 0)) return CG_ERR_UNSUPPORTED;
   GradOperand g; CG_TRY(pack_grad_operand(gy, N, H, W, Co, k, &g, gb_acc));
   if (gb_acc && bias_done) *bias_done = 1;
-  CG_TRY(conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done, xq_prepacked));
+  // weight-gradient chain (MMA kernel, split sum, layout change) on the side stream: nothing reads it before the model's
+  // backward ends, while the input gradient below is on the critical path
+  // (only when the result goes straight into the Torch-layout gradient: the packed form then lives in the side stream's scratch)
+  const int side = gW_acc ? side_begin() : 0;
+  int wst = CG_OK, wdone = 0;
+  if (side) {
+    float* gWp_side = (float*)workspace(sizeof(float) * (size_t)k * k * Ci * Co + 256);
+    wst = gWp_side ? conv_wgrad_tc_impl(x, g, gWp_side, N, H, W, Ci, Co, k, gW_acc, &wdone, xq_prepacked) : CG_ERR_CUDA;
+    if (wst == CG_OK && !wdone) wst = set_err(CG_ERR_STATE, "side-stream weight gradient was not accumulated");
+    if (done) *done = wdone;
+    int est = side_end(); if (wst == CG_OK) wst = est;
+  } else wst = conv_wgrad_tc_impl(x, g, gWp_out, N, H, W, Ci, Co, k, gW_acc, done, xq_prepacked);
+  CG_TRY(wst);
   // dgrad = forward convolution of gy (Co channels in) with the flipped weights (Ci channels out)
   return conv_tc_run<2>(gy, Wd, nullptr, gx, N, H, W, Co, Ci, k, g.scale2, g.gq);
 }

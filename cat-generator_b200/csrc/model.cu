@@ -203,6 +203,7 @@ static int layer_fwd(cg_model* m, int li, const float* x, float* y, int N, int H
 // accumulates dW, db into the flat gradient; gx may be null
 static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float* gx, int N, int H, int W, const uint8_t* xq = nullptr) {   // xq: cached operand for x
   cg_layer& L = m->layers[li];
+  if (m->skip_param_grads) return gx ? conv_dgrad(gy, L.Wd, gx, N, H, W, L.s.Ci, L.s.Co, L.s.k) : CG_OK;   // same dgrad kernel and operand as below
   long M = (long)N * H * W;
   float* gwp = gw_scratch(m); NN(gwp);
   // plain convolutions let the engine add straight into the Torch-layout gradient; Linear layers beside an nn.View need the permuting unpack
@@ -327,6 +328,7 @@ int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
   CG_TRY(prelu_bwd(g->lin, gcur, g->P + g->oLpw, glin, g->G + g->oLpw, B * F0));
   float* gz = gz_dev ? gz_dev : BW(g, (size_t)B * g->nz); NN(gz);
   CG_TRY(layer_bwd(g, g->lin_layer, g->z, glin, gz, B, 1, 1));
+  CG_TRY(side_wait_all());   // parameter gradients are complete when this returns (stream order)
   return CG_OK;
 }
 
@@ -453,6 +455,9 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
   return CG_OK;
 }
 
+// where a PReLU weight gradient goes (nowhere when parameter gradients are skipped)
+static inline float* PG(cg_model* m, long off) { return m->skip_param_grads ? nullptr : m->G + off; }
+
 int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   if (!d->B) return set_err(CG_ERR_STATE, "D backward before forward");
   d->nbw = 0; int B = d->B, C = d->C;
@@ -463,7 +468,7 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   float* gh2 = BW(d, B); NN(gh2); CG_TRY(sigmoid_bwd(d->hsig, gout_dev, gh2, B));
   float* ghd = BW(d, (size_t)B * 256); NN(ghd); CG_TRY(layer_bwd(d, d->h2, d->hd, gh2, ghd, B, 1, 1));
   float* gha1 = BW(d, (size_t)B * 256); NN(gha1); CG_TRY(mask_elems(ghd, mk_fc, gha1, (long)B * 256));
-  float* gh1 = BW(d, (size_t)B * 256); NN(gh1); CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, d->G + d->hpw, (long)B * 256));
+  float* gh1 = BW(d, (size_t)B * 256); NN(gh1); CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, PG(d, d->hpw), (long)B * 256));
   float* gcatd = BW(d, (size_t)B * 20480); NN(gcatd); CG_TRY(layer_bwd(d, d->h1, d->catd, gh1, gcatd, B, 1, 1));
   float* gcat = BW(d, (size_t)B * 20480); NN(gcat); CG_TRY(mask_channels(gcatd, mk_head, gcat, B, 64, 320));
   long nT = (long)B * 256 * 64;
@@ -476,11 +481,11 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
     int Co = b < 3 ? 64 : 128;
     long n2 = (long)B * 64 * Co, n1 = n2 * 4;
     float* go = BW(d, n2); NN(go); CG_TRY(copy_channels(gcat, go, (long)B * 64, Co, 320, b * 64, 1));
-    float* gc2 = BW(d, n2); NN(gc2); CG_TRY(prelu_bwd(d->bc2[b], go, d->P + d->bpw2[b], gc2, d->G + d->bpw2[b], n2));
+    float* gc2 = BW(d, n2); NN(gc2); CG_TRY(prelu_bwd(d->bc2[b], go, d->P + d->bpw2[b], gc2, PG(d, d->bpw2[b]), n2));
     float* gdr = BW(d, n2); NN(gdr); CG_TRY(layer_bwd(d, d->b2[b], d->bdr[b], gc2, gdr, B, 8, 8));
     float* gmp = BW(d, n2); NN(gmp); CG_TRY(mask_channels(gdr, mk, gmp, B, 64, Co)); mk += (long)B * Co;
     float* ga1 = BW(d, n1); NN(ga1); CG_TRY(maxpool2_bwd(gmp, d->bidx[b], ga1, B, 16, 16, Co));
-    float* gc1 = BW(d, n1); NN(gc1); CG_TRY(prelu_bwd(d->bc1[b], ga1, d->P + d->bpw1[b], gc1, d->G + d->bpw1[b], n1));
+    float* gc1 = BW(d, n1); NN(gc1); CG_TRY(prelu_bwd(d->bc1[b], ga1, d->P + d->bpw1[b], gc1, PG(d, d->bpw1[b]), n1));
     const float* bin = b < 3 ? d->stn[b + 1].out : d->T;
     float* gbin = BW(d, nT); NN(gbin); CG_TRY(layer_bwd(d, d->b1[b], bin, gc1, gbin, B, 16, 16));
     if (b < 3) {
@@ -494,13 +499,14 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   float* gtp = BW(d, nT); NN(gtp); CG_TRY(mask_channels(gT, mk_trunk, gtp, B, 256, 64));
   long n64 = (long)B * 1024 * 64;
   float* gta2 = BW(d, n64); NN(gta2); CG_TRY(avgpool2_bwd(gtp, gta2, B, 32, 32, 64));
-  float* gtc2 = BW(d, n64); NN(gtc2); CG_TRY(prelu_bwd(d->tc2, gta2, d->P + d->t2pw, gtc2, d->G + d->t2pw, n64));
+  float* gtc2 = BW(d, n64); NN(gtc2); CG_TRY(prelu_bwd(d->tc2, gta2, d->P + d->t2pw, gtc2, PG(d, d->t2pw), n64));
   float* gta1 = BW(d, n64); NN(gta1); CG_TRY(layer_bwd(d, d->t2, d->ta1, gtc2, gta1, B, 32, 32));
-  float* gtc1 = BW(d, n64); NN(gtc1); CG_TRY(prelu_bwd(d->tc1, gta1, d->P + d->t1pw, gtc1, d->G + d->t1pw, n64));
+  float* gtc1 = BW(d, n64); NN(gtc1); CG_TRY(prelu_bwd(d->tc1, gta1, d->P + d->t1pw, gtc1, PG(d, d->t1pw), n64));
   float* gs0 = BW(d, (size_t)B * 1024 * C); NN(gs0); CG_TRY(layer_bwd(d, d->t1, d->stn[0].out, gtc1, gs0, B, 32, 32));
   float* gin = BW(d, (size_t)B * 1024 * C); NN(gin);
   CG_TRY(stn_backward(d, &d->stn[0], gs0, gin, B));
   if (gx_nchw) CG_TRY(nhwc_to_nchw(gin, gx_nchw, B, C, 1024));        // MODEL_D.modules[1].gradInput (adversarial.lua:193)
+  CG_TRY(side_wait_all());   // parameter gradients are complete when this returns (stream order)
   return CG_OK;
 }
 

@@ -30,6 +30,7 @@ struct cg_model {
   uint8_t* wq = nullptr; cg::PackJob* jobs_dev = nullptr; int njobs = 0, repack_blocks = 0;   // fp16 weight slices + the one-launch repack table
   bool dirty = true;                        // packed operands stale w.r.t. P
   int training = 1;
+  int skip_param_grads = 0;                 // backward computes input gradients only (D inside fevalG: its parameter gradients are never read)
   uint64_t seed = 0, rng_offset = 0;          // rng_offset: host counter used only while initialising parameters
   unsigned long long* rng_dev = nullptr;      // Philox offset of the dropout masks, in device memory (graph replay)
   std::vector<cg::DBuf> fw, bw; int nfw = 0, nbw = 0;
@@ -60,7 +61,7 @@ struct cg_trainer {
   cg::DBuf inputs, targets, samples, dout, df, gimg, scal, stage;
   // CUDA-graph replay of the step (capi.cu): fixed input buffers + one instantiated graph per step configuration
   cg::DBuf gin;
-  struct StepGraph { cg_step_cfg cfg; int warm = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  struct StepGraph { cg_step_cfg cfg; int engine = 0, elim = 0, lanes = 0; int warm = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
   std::vector<StepGraph> graphs;
 };
 

@@ -65,6 +65,11 @@ int         cg_get_graph_mode(void);
 /* conv engine for shapes the tensor-core path supports: 0 = fp32 CUDA-core fallback only, 1 = tcgen05 (default) */
 int         cg_set_conv_engine(int engine);
 int         cg_get_conv_engine(void);
+/* cg_train_step*: inside fevalG the reference's MODEL_D:backward (adversarial.lua:193) also accumulates D's parameter gradients,
+   which the next fevalD zeroes unread (adversarial.lua:78).  1 (default): that dead accumulation is skipped -- parameters,
+   optimiser state, losses and d_out are bit-identical either way; 0: keep it, so D's gradient vector after a step holds
+   what Torch's gradParameters would. */
+int         cg_set_dead_grad_elim(int on);
 
 /* ------------------------------------------------------------------ models */
 /* replaces models.create_G(dimensions, noiseDim) / models.create_D(dimensions, cuda); H=W=32.

@@ -61,7 +61,7 @@ void* workspace(size_t bytes) { return grow(&ctx().ws, &ctx().ws_bytes, bytes); 
 void* workspace2(size_t bytes) { return grow(&ctx().ws2, &ctx().ws2_bytes, bytes); }
 void* workspace3(size_t bytes) { return grow(&ctx().ws3, &ctx().ws3_bytes, bytes); }
 void* workspace4(size_t bytes) { return grow(&ctx().ws4, &ctx().ws4_bytes, bytes); }
-int lanes_fork() {
+int lanes_fork(int first, int n) {
   Ctx& c = ctx();
   if (!c.lanes_on) return CG_OK;
   if (c.lane != -1) return set_err(CG_ERR_STATE, "lanes_fork inside a lane");
@@ -70,7 +70,7 @@ int lanes_fork() {
     for (auto& L : c.lanes) { CG_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)); CG_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
   }
   CG_CUDA(cudaEventRecord(c.fork_ev, c.stream));
-  for (auto& L : c.lanes) CG_CUDA(cudaStreamWaitEvent(L.stream, c.fork_ev, 0));
+  for (int b = first; b < first + n; ++b) CG_CUDA(cudaStreamWaitEvent(c.lanes[b].stream, c.fork_ev, 0));
   return CG_OK;
 }
 int lane_enter(int b) {
@@ -93,12 +93,12 @@ int lane_exit() {
   c.lane = -1;
   return CG_OK;
 }
-int lanes_join() {
+int lanes_join(int first, int n) {
   Ctx& c = ctx();
   if (!c.lanes_on) return CG_OK;
   if (c.lane != -1) return set_err(CG_ERR_STATE, "lanes_join inside a lane");
-  for (auto& L : c.lanes) { CG_CUDA(cudaEventRecord(L.done, L.stream)); CG_CUDA(cudaStreamWaitEvent(c.stream, L.done, 0)); }
-  for (int b = 1; b <= Ctx::kLanes; ++b) if (c.side[b].pending) { CG_CUDA(cudaStreamWaitEvent(c.stream, c.side[b].done, 0)); c.side[b].pending = false; }
+  for (int b = first; b < first + n; ++b) { Ctx::Lane& L = c.lanes[b]; CG_CUDA(cudaEventRecord(L.done, L.stream)); CG_CUDA(cudaStreamWaitEvent(c.stream, L.done, 0)); }
+  for (int b = first + 1; b <= first + n; ++b) if (c.side[b].pending) { CG_CUDA(cudaStreamWaitEvent(c.stream, c.side[b].done, 0)); c.side[b].pending = false; }
   return CG_OK;
 }
 int side_begin() {
@@ -426,6 +426,8 @@ int cg_dist_allreduce_grads(cg_model* m) {
 }
 
 // one adversarial.train loop body on device-resident inputs.  scal: [lossD(d_iters), pen(d_iters), lossG(g_iters), pen(g_iters)]
+struct LaneGuard { int status; bool in; explicit LaneGuard(int b) : status(cg::lane_enter(b)), in(status == CG_OK) {} ~LaneGuard() { if (in) cg::lane_exit(); } };
+
 static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* real, const float* zD, const float* zG, float* lossD, float* lossG) {
   cg_model *G = t->G, *D = t->D;
   int B = c->B, hB = B / 2, C = G->C, nz = G->nz; size_t img = (size_t)C * 1024;
@@ -436,10 +438,20 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
   float* tgtD = t->targets.p; float* tgtG = t->targets.p + B;
   CG_TRY(fill(tgtD, 1.f, hB)); CG_TRY(fill(tgtD + hB, 0.f, B - hB)); CG_TRY(fill(tgtG, 1.f, B));   // Y_NOT_GENERATOR=1, Y_GENERATOR=0 (train.lua:70-71)
   int si = 0;
+  bool g_ahead = false;
   for (int k = 0; k < c->d_iters; ++k) {
     // (1.1) real half, (1.2) fake half from a separate G forward on B/2 noise vectors (adversarial.lua:223-238)
     CG_CUDA(cudaMemcpyAsync(t->inputs.p, real + (size_t)k * hB * img, sizeof(float) * hB * img, cudaMemcpyDeviceToDevice, ctx().stream));
     CG_TRY(G_forward_dev(G, zD + (size_t)k * hB * nz, hB, t->inputs.p + hB * img));
+    // fevalG's generator forward depends on nothing fevalD changes (G's parameters move only in fevalG; its BN running
+    // statistics are updated in issue order): start it now on its own lane, beside D's forward/backward/Adam below.
+    if (k == c->d_iters - 1 && c->g_iters > 0 && ctx().lanes_on) {
+      CG_TRY(lanes_fork(4, 1));
+      int st;
+      { LaneGuard lane(4); st = lane.status; if (st == CG_OK) st = G_forward_dev(G, zG, B, t->samples.p); }
+      CG_TRY(st);
+      g_ahead = true;
+    }
     // fevalD (adversarial.lua:72-167)
     CG_CUDA(cudaMemsetAsync(D->G, 0, sizeof(float) * D->np, ctx().stream));
     CG_TRY(D_forward_dev(D, t->inputs.p, B, t->dout.p, nullptr));
@@ -453,7 +465,8 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
   for (int k = 0; k < c->g_iters; ++k) {
     // fevalG_on_D (adversarial.lua:171-215)
     CG_CUDA(cudaMemsetAsync(G->G, 0, sizeof(float) * G->np, ctx().stream));
-    CG_TRY(G_forward_dev(G, zG + (size_t)k * B * nz, B, t->samples.p));
+    if (k == 0 && g_ahead) CG_TRY(lanes_join(4, 1));
+    else CG_TRY(G_forward_dev(G, zG + (size_t)k * B * nz, B, t->samples.p));
     CG_TRY(D_forward_dev(D, t->samples.p, B, nullptr, nullptr));   // t->dout keeps the last D-phase outputs for d_out
     float* dsig = D->hsig;
     CG_TRY(bce(dsig, tgtG, B, t->scal.p + si, t->df.p));

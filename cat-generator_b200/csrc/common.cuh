@@ -32,7 +32,7 @@ struct Ctx {
   // scratch, forked from / joined to `stream` by events -- which CUDA-graph capture records as parallel paths.  lane_enter()
   // swaps `stream`, ws, ws3, ws4 with the lane's, so every launcher keeps using ctx().stream / workspace*() unchanged.
   struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; void *ws = nullptr, *ws3 = nullptr, *ws4 = nullptr; size_t ws_bytes = 0, ws3_bytes = 0, ws4_bytes = 0; };
-  static constexpr int kLanes = 4;
+  static constexpr int kLanes = 5;   // 0-3: D's branches; 4: the generator forward of fevalG, issued ahead (capi.cu: train_step_core)
   Lane lanes[kLanes], saved;
   int lane = -1;                // -1: the main stream
   int lanes_on = 1;             // CATGEN_LANES=0 serialises the branches on the main stream
@@ -64,10 +64,10 @@ void* workspace3(size_t bytes);   // device scratch #3: tensor-core operand pack
                                   // reallocates, and ws2 pointers are live across the whole forward/backward call)
 void* workspace4(size_t bytes);   // device scratch #4: the packed gradient operand shared by dgrad and wgrad of one layer (outlives both runs' ws3 use)
 void* pinned(size_t bytes);       // pinned host staging
-int lanes_fork();                 // lanes may start after everything issued on the main stream so far
+int lanes_fork(int first = 0, int n = 4);   // lanes [first, first+n) may start after everything issued on the main stream so far
 int lane_enter(int b);            // route launches + scratch to lane b (no-op when lanes are off)
 int lane_exit();
-int lanes_join();                 // the main stream waits for every lane (and the lanes' side streams)
+int lanes_join(int first = 0, int n = 4);   // the main stream waits for those lanes (and their side streams)
 int side_begin();                 // 1: launches now go to this stream's side stream (ordered after everything issued so far); 0: side streams off
 int side_end();                   // back to the owning stream; the side work is pending
 int side_wait();                  // the owning stream waits for its pending side work (before reusing what that work reads)

@@ -296,6 +296,9 @@ def main():
     # ---- per-kernel durations (CUDA events around every launch) on a separate short pass: events perturb the step time
     roof = None
     kp = min(K, 3)
+    # one stream, program order: with the step's concurrent lanes on, an event-bracketed launch also counts the time it
+    # shares the SMs with other lanes' kernels, which is not that kernel's duration
+    lib.check(L.cg_set_concurrency(0))
     if rank == 0:
         lib.check(L.cg_profile_enable(1))
     # EVERY rank runs these steps: each contains the gradient all-reduces, and a rank-0-only pass deadlocked the
@@ -303,6 +306,7 @@ def main():
     for i in range(kp):
         dev_step(W + i, False)
     barrier()
+    lib.check(L.cg_set_concurrency(1))
     if rank == 0:
         buf = C.create_string_buffer(1 << 16)
         lib.check(L.cg_profile_report(buf, len(buf)))

@@ -267,6 +267,7 @@ int cg_set_graph_mode(int on) { ctx().graph_mode = on ? 1 : 0; return CG_OK; }
 int cg_get_graph_mode(void) { return ctx().graph_mode; }
 int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
 int cg_get_conv_engine(void) { return ctx().conv_engine; }
+int cg_set_concurrency(int on) { CG_REQUIRE_INIT(); if (ctx().lane != -1 || ctx().in_side) return set_err(CG_ERR_STATE, "cg_set_concurrency inside a lane"); cudaStreamSynchronize(ctx().stream); ctx().lanes_on = ctx().side_on = on ? 1 : 0; return CG_OK; }
 int cg_set_dead_grad_elim(int on) { ctx().dead_grad_elim = on ? 1 : 0; return CG_OK; }
 
 // ------------------------------------------------------------------ models

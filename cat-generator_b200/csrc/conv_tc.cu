@@ -253,6 +253,9 @@ int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks) {
 
 // ------------------------------------------------------------------ the kernel
 struct TcParams {
+  int nostore;      // experiments (CATGEN_TC_DBG=2): the epilogue reads TMEM but does not store (timing only, wrong results)
+  long long* dbg;   // experiments (CATGEN_TC_DBG=1): per-CTA clock64 timeline, 8 values
+  int rot;          // 1: each CTA walks the filter taps from its own starting tap (spreads the CTAs' weight-slice reads over L2)
   const uint8_t* xq; const uint8_t* wq; const float* bias; float* y;
   const float* scale2;                 // [scale, 1/scale] of a gradient-valued input (device), or null
   int N, H, W, Ci, Co, k, p, Hq, Wq;   // Ci/Co: PADDED channel counts the kernel iterates over; Hq/Wq: padded dims of xq
@@ -273,6 +276,8 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
   __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[8], bar_wempty[8], bar_acc;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* dbg = P.dbg ? P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && tid == 0) dbg[0] = clock64();
   uint8_t* patch0 = smem;                                      // patch buffers [2][TL]
   uint8_t* wring = smem + 2 * (size_t)P.TL * P.patch_bytes;    // S weight slices
 
@@ -315,11 +320,15 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
       // slices for all Co are stored [slice][c][Co][PER]; a CTA that owns NB < Co columns copies per plane
       const int PL = KB / PER;
       int st = 0; uint32_t ph = 0;
+      const int per_cb = kk * nsub, rot_s = P.rot ? (int)((blockIdx.x * 7u) % (unsigned)kk) * nsub : 0;
+      int cb_base = 0, within = rot_s;                  // slice order inside a channel block starts at this CTA's own tap
       for (int s = 0; s < nslices; ++s, st = (st + 1 == P.S) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
         mbar_wait(&bar_wempty[st], ph ^ 1);
         mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
         uint8_t* dst = wring + (size_t)st * P.slice_bytes;
-        const uint8_t* src = P.wq + (size_t)s * PL * P.Co * 16;
+        const uint8_t* src = P.wq + (size_t)(cb_base + within) * PL * P.Co * 16;
+        if (++within == per_cb) within = 0;
+        if (within == rot_s) cb_base += per_cb;
         if (P.NB == P.Co) bulk_g2s(dst, src, P.slice_bytes, &bar_wfull[st]);
         else for (int c = 0; c < PL; ++c) bulk_g2s(dst + (size_t)c * P.NB * 16, src + ((size_t)c * P.Co + co0) * 16, P.NB * 16, &bar_wfull[st]);
       }
@@ -352,18 +361,27 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
       const uint32_t a_kstep = 2 * plane16, b_kstep = 2 * (b_lbo >> 4), a_sub = (uint32_t)(KB / PER) * plane16;
       const uint32_t w_lo0 = desc_lo(smem_u32(wring), b_lbo);
       const int S = P.S, k = P.k, NB = P.NB;
+      const int rot_tap = P.rot ? (int)((blockIdx.x * 7u) % (unsigned)kk) : 0;
       uint32_t st = 0, wph = 0, acc0 = 0;
+      long long w_wait = 0, p_wait = 0, tq = 0;
+      if (dbg && warp == 6) dbg[1] = clock64();
       for (int cb = 0; cb < P.ncb; ++cb) {
         const int buf = cb & 1;
+        if (dbg) tq = clock64();
         mbar_wait(&bar_pfull[buf], (cb >> 1) & 1);
+        if (dbg) p_wait += clock64() - tq;
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t p_lo0 = desc_lo(smem_u32(patch0 + (size_t)(buf * P.TL) * P.patch_bytes), plane_bytes);
-        uint32_t row_lo = p_lo0;                                  // start of filter row ky in 16-byte units
-        for (int ky = 0; ky < k; ++ky, row_lo += (uint32_t)Wp) {
-          for (int kx = 0; kx < k; ++kx) {
-            uint32_t a_lo = row_lo + (uint32_t)kx;
+        // filter taps in this CTA's own cyclic order (same order as the weight producer); ky/kx kept incrementally
+        int ky = rot_tap / k, kx = rot_tap - ky * k;
+        for (int t = 0; t < kk; ++t) {
+          {
+            uint32_t a_lo = p_lo0 + (uint32_t)(ky * Wp + kx);
+            if (++kx == k) { kx = 0; if (++ky == k) ky = 0; }
             for (int sub = 0; sub < nsub; ++sub, a_lo += a_sub) {
+              if (dbg) tq = clock64();
               mbar_wait(&bar_wfull[st], wph);
+              if (dbg) w_wait += clock64() - tq;
               asm volatile("tcgen05.fence::after_thread_sync;");
               const uint32_t w_lo = w_lo0 + st * slice16;
               if (have_tile) {
@@ -382,6 +400,7 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
         umma_commit(&bar_pempty[buf]);
       }
       umma_commit(&bar_acc);
+      if (dbg && warp == 6) { dbg[2] = clock64(); dbg[3] = w_wait; dbg[4] = p_wait; }
     }
   }
 
@@ -389,11 +408,59 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
     // ===== epilogue: TMEM -> registers -> (+bias) -> NHWC fp32.  warp w owns TMEM lanes 32w..32w+31 = pixels.
     mbar_wait(&bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;");
+    if (dbg && tid == 0) dbg[5] = clock64();
     const int m = warp * 32 + lane;
     const bool vec = (P.Cor & 3) == 0;
     const float inv = P.scale2 ? P.scale2[1] : 1.f;
+    // Stores: a lane holds one PIXEL's columns, so storing from the TMEM layout writes 16 bytes per lane at a 4*Cout-byte stride
+    // -- measured on conv3: 26.7k of a CTA's 108k cycles in this epilogue, 2.8k with the stores removed
+    // (profiles/r01_conv3_cta_timeline*.txt).  Full-width column blocks therefore go through a per-warp shared-memory tile
+    // (the patch buffers are idle once bar_acc has fired) and leave as whole 128-byte lines: 8 lanes per pixel, 4 pixels per store.
+    float* stage = reinterpret_cast<float*>(patch0) + warp * (32 * 36);          // 32 pixel rows x (32 + 4 pad) floats
+    const bool wide = vec && (P.NB & 31) == 0 && !P.nostore;
     for (int tl = 0; tl < ntl; ++tl) {
     int n, y0, x0; tile_xy(tl, n, y0, x0);
+    if (wide) {
+      for (int c0 = 0; c0 < P.NB; c0 += 32) {
+        uint32_t v[32];
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        if (co0 + c0 + 32 <= P.Cor) {                    // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co0 + c0 + j] : 0.f);
+            o.y = __uint_as_float(v[j + 1]) * inv + (P.bias ? P.bias[co0 + c0 + j + 1] : 0.f);
+            o.z = __uint_as_float(v[j + 2]) * inv + (P.bias ? P.bias[co0 + c0 + j + 2] : 0.f);
+            o.w = __uint_as_float(v[j + 3]) * inv + (P.bias ? P.bias[co0 + c0 + j + 3] : 0.f);
+            *reinterpret_cast<float4*>(stage + lane * 36 + j) = o;
+          }
+          __syncwarp();
+          const int q = (lane & 7) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int pl = i * 4 + (lane >> 3), mm = warp * 32 + pl;
+            const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+            float4 o = *reinterpret_cast<const float4*>(stage + pl * 36 + q);
+            if (oy < P.H && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q) = o;
+          }
+          __syncwarp();
+        } else {                                          // padded columns past Cout: per-lane scalar stores of the real ones
+          const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+          if (oy < P.H && ox < P.W) {
+            float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+            for (int j = 0; j < 32; ++j) { int co = co0 + c0 + j; if (co < P.Cor) out[c0 + j] = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co] : 0.f); }
+          }
+        }
+      }
+      continue;
+    }
     int oy = y0 + (m >> 3), ox = x0 + (m & 7);
     bool valid = oy < P.H && ox < P.W;
     float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
@@ -405,7 +472,8 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                    : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;");
-      if (valid && vec && co0 + c0 + 16 <= P.Cor) {
+      if (P.nostore) { if (v[0] == 0x7fc12345u) out[0] = 1.f; }
+      else if (valid && vec && co0 + c0 + 16 <= P.Cor) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 o;
@@ -424,6 +492,7 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(TcParams P, const __grid_con
       }
     }
     }   // tiles
+    if (dbg && tid == 0) dbg[6] = clock64();
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -488,6 +557,8 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   if (!CB) return CG_ERR_UNSUPPORTED;
   size_t patch_bytes = (size_t)(CB / PER) * Hp * Wpx * 16;
   int S = (int)((216 * 1024 - 2 * TL * patch_bytes) / slice_bytes); if (S > 8) S = 8;
+  static const int s_cap = getenv("CATGEN_TC_RING") ? atoi(getenv("CATGEN_TC_RING")) : 8;   // experiments: cap the weight ring depth
+  if (S > s_cap && s_cap >= 2) S = s_cap;
   if (S < 2) return CG_ERR_UNSUPPORTED;
   size_t smem = 2 * TL * patch_bytes + (size_t)S * slice_bytes;
   // operand buffers: activations then weight slices (16-byte aligned)
@@ -505,6 +576,13 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
     CG_LAUNCH(k_pack_wslices<ES>, grid1d(nw, 256), 256, 0, Wp, wqb, nw, Cir, Cor, Co, kk, CB);
     wq = wqb;
   }
+  static const bool dbg_on = getenv("CATGEN_TC_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 8 * 65536);
+  P.dbg = dbg_on ? dbg_buf : nullptr;
+  P.nostore = (dbg_on && atoi(getenv("CATGEN_TC_DBG")) == 2) ? 1 : 0;
+  static const int rot_on = getenv("CATGEN_TC_ROT") ? atoi(getenv("CATGEN_TC_ROT")) : 0;
+  P.rot = rot_on;
   P.xq = xq; P.wq = wq; P.bias = bias; P.y = y; P.scale2 = scale2;
   P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
   P.CB = CB; P.ncb = Ci / CB; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S; P.TL = TL; P.ntiles = ntiles;
@@ -521,6 +599,20 @@ static int conv_tc_run(const float* x, const float* Wp, const float* bias, float
   CG_TRY(make_patch_tmap(&tmx, xq, ES, N, Ci / PER, Hq, Wq, Hp, Wpx, CB / PER));
   if (ES == 2) CG_LAUNCH(k_conv_tc<2>, grid, 256, smem, P, tmx);
   else CG_LAUNCH(k_conv_tc<4>, grid, 256, smem, P, tmx);
+  if (dbg_on && dbg_buf && (long)grid.x * grid.y <= 65536) {   // experiments only: where does a CTA's time go (cycles, mean over CTAs)
+    cudaStreamSynchronize(ctx().stream);
+    size_t n = (size_t)grid.x * grid.y;
+    std::vector<long long> h(n * 8);
+    cudaMemcpy(h.data(), dbg_buf, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+    double tot = 0, pro = 0, loop = 0, ww = 0, pw = 0, drain = 0, epi = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const long long* d = &h[i * 8];
+      tot += d[6] - d[0]; pro += d[1] - d[0]; loop += d[2] - d[1]; ww += d[3]; pw += d[4]; drain += d[5] - d[2]; epi += d[6] - d[5];
+    }
+    fprintf(stderr, "[tc dbg] N=%d HxW=%dx%d Ci=%d Co=%d k=%d grid=%ux%u TL=%d CB=%d NB=%d S=%d | per CTA cycles: total %.0f = prologue %.0f + issue loop %.0f (waiting: weights %.0f, patch %.0f) + drain %.0f + epilogue %.0f | MMA floor %.0f\n",
+            N, H, W, Cir, Cor, k, grid.x, grid.y, TL, CB, NB, S, tot / n, pro / n, loop / n, ww / n, pw / n, drain / n, epi / n,
+            (double)TL * (Ci / (128 / ES)) * kk * 4 * (128.0 * NB / 256.0));
+  }
   return CG_OK;
 }
 

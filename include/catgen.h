@@ -70,6 +70,11 @@ int         cg_get_conv_engine(void);
    optimiser state, losses and d_out are bit-identical either way; 0: keep it, so D's gradient vector after a step holds
    what Torch's gradParameters would. */
 int         cg_set_dead_grad_elim(int on);
+/* 1 (default): independent parts of a step are issued on concurrent streams -- D32_st3's four transformer branches, each layer's
+   weight-gradient chain beside its input-gradient conv, fevalG's generator forward beside fevalD -- joined by events (which graph
+   capture records as parallel paths).  0: everything on one stream, in program order (per-kernel timing, debugging).
+   Environment: CATGEN_LANES=0 / CATGEN_SIDE=0 set the initial state of the two mechanisms separately. */
+int         cg_set_concurrency(int on);
 
 /* ------------------------------------------------------------------ models */
 /* replaces models.create_G(dimensions, noiseDim) / models.create_D(dimensions, cuda); H=W=32.

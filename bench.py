@@ -328,6 +328,8 @@ def main():
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["bytes"] else None
             roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (ach / pk["hbm_gbs"]) if ach else None,
                     "traffic": None, "peak_source": pk["source"], "share_of_step": top["ms"] / tot}
+        roof["timed"] = ("CUDA events around every launch of %d eager steps issued on ONE stream (cg_set_concurrency(0)); the timed region itself "
+                         "replays the step as one CUDA graph with concurrent lanes, where a bracketed launch would also count time shared with other lanes" % kp)
         roof["top5"] = [{"kernel": k["kernel"], "share": round(k["ms"] / tot, 4), "launches_per_step": k["launches"] / kp} for k in prof[:5]]
         roof["kernels"] = [{"kernel": k["kernel"], "ms_per_step": round(k["ms"] / kp, 4), "launches_per_step": k["launches"] / kp} for k in prof[:30]]
 

@@ -724,7 +724,7 @@ struct TcWParams {
   uint32_t patch_bytes, patch_load_bytes, g_bytes;
 };
 
-__global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmg) {
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc(TcWParams P, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmg) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -740,8 +740,10 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
   const long t0 = (long)P.tiles_total * z / P.Z, t1 = (long)P.tiles_total * (z + 1) / P.Z;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
-    mbar_init(&bar_acc, 1);
+    // two MMA issuers (warps 6, 7) take alternate filter taps: one thread retires an M=128 MMA per ~84 cycles against the pipe's
+    // 64 (tools/tc_rate.cu, profiles/r01_tc_rate.txt); a stage is free / the accumulators are complete when BOTH have committed
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 2); }
+    mbar_init(&bar_acc, 2);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   int ncols = 32; while (ncols < P.TG * P.NB) ncols <<= 1;
@@ -783,15 +785,15 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
         tma_patch_4d(smem + (size_t)buf * stage_bytes, &tmx, tx * 8 * 8, ty * 16, cib * 16, n, &bar_full[buf]);
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 6 || warp == 7) {
     if (lane == 0) {
       // MN-major A and B (bits 15, 16), fp16, fp32 accumulate, M = 128, N = NB
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)Wp * 16;                        // k-group = next patch row; mn chunk (SBO) = next ci plane
       const uint32_t a_hi = desc_hi(plane_bytes), b_hi = desc_hi(2048); // B: k-group (LBO) = next 8-px row (128 B); mn chunk = next co plane
       const uint32_t a_kstep = 2 * (uint32_t)Wp, b_kstep = 16;          // two k-groups per instruction, in 16-byte units
-      const int k = P.k, NB = P.NB;
-      const int ky0 = tap0 / k, kx0 = tap0 - ky0 * k;                   // the only division: once per CTA
+      const int k = P.k, NB = P.NB, me = warp - 6;
+      int ky0 = (tap0 + me) / k, kx0 = (tap0 + me) - ky0 * k;           // this issuer's first tap; the only division, once per CTA
       uint32_t acc0 = 0;
       int it = 0;
       for (long t = t0; t < t1; ++t, ++it) {
@@ -800,14 +802,14 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t pbase = smem_u32(smem + (size_t)buf * stage_bytes);
         const uint32_t p_lo = desc_lo(pbase, a_lbo), g_lo = desc_lo(pbase + P.patch_bytes, 128);
-        int ky = ky0, kx = kx0; uint32_t tm = tmem;
-        for (int tl = 0; tl < ntap; ++tl, tm += (uint32_t)NB) {
+        int ky = ky0, kx = kx0; uint32_t tm = tmem + (uint32_t)(me * NB);
+        for (int tl = me; tl < ntap; tl += 2, tm += (uint32_t)(2 * NB)) {
           const uint32_t a_lo = p_lo + (uint32_t)(ky * Wp + kx);
           umma<2>(tm, desc64(a_lo, a_hi), desc64(g_lo, b_hi), idesc, acc0);
 #pragma unroll
           for (int ks = 1; ks < 8; ++ks)
             umma<2>(tm, desc64(a_lo + (uint32_t)ks * a_kstep, a_hi), desc64(g_lo + (uint32_t)ks * b_kstep, b_hi), idesc, 1u);
-          if (++kx == k) { kx = 0; ++ky; }
+          kx += 2; while (kx >= k) { kx -= k; ++ky; }
         }
         acc0 = 1u;
         umma_commit(&bar_empty[buf]);
@@ -825,8 +827,45 @@ __global__ void __launch_bounds__(224, 1) k_wgrad_tc(TcWParams P, const __grid_c
     const bool row_ok = ci_l < P.cim && ci < P.Cir;
     const bool valid = row_ok && t1 > t0;
     const bool vec = (P.Cor & 3) == 0;
+    // full-width column blocks leave through a per-warp shared-memory tile as whole 128-byte lines (see k_conv_tc's epilogue);
+    // the stage buffers are idle once bar_acc has fired
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    const bool wide = vec && (P.NB & 31) == 0;
     for (int tl = 0; tl < ntap; ++tl) {
       float* out = P.part + ((size_t)z * kk * P.Cir + (size_t)(tap0 + tl) * P.Cir + (size_t)ci) * P.Cor + (size_t)cob * P.NB;
+      if (wide) {
+        for (int c0 = 0; c0 < P.NB; c0 += 32) {
+          uint32_t v[32];
+          uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                       : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;");
+          const int cbase = cob * P.NB + c0;
+          if (cbase + 32 <= P.Cor) {                     // warp-uniform
+            const float sc = (t1 > t0) ? inv : 0.f;       // empty pixel range: zeros
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(__uint_as_float(v[j]) * sc, __uint_as_float(v[j + 1]) * sc, __uint_as_float(v[j + 2]) * sc, __uint_as_float(v[j + 3]) * sc);
+            __syncwarp();
+            const int q = (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int pl = i * 4 + (lane >> 3), cl = warp * 32 + pl, cg_ = cib * 128 + cl;
+              float4 o = *reinterpret_cast<const float4*>(stage + pl * 36 + q);
+              if (cl < P.cim && cg_ < P.Cir)
+                *reinterpret_cast<float4*>(P.part + ((size_t)z * kk * P.Cir + (size_t)(tap0 + tl) * P.Cir + (size_t)cg_) * P.Cor + (size_t)cbase + q) = o;
+            }
+            __syncwarp();
+          } else if (row_ok) {
+            for (int j = 0; j < 32; ++j) if (cbase + j < P.Cor) out[c0 + j] = valid ? __uint_as_float(v[j]) * inv : 0.f;
+          }
+        }
+        continue;
+      }
       for (int c0 = 0; c0 < P.NB; c0 += 16) {
         uint32_t v[16];
         uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
@@ -917,7 +956,7 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   CUtensorMap tmx, tmg;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, P.cim / 8));
   CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
-  CG_LAUNCH(k_wgrad_tc, grid, 224, smem, P, tmx, tmg);
+  CG_LAUNCH(k_wgrad_tc, grid, 256, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
   CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // fully parallel, fixed z order
   if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; }   // layout change only

@@ -517,6 +517,50 @@ def test_graph_replay_matches_eager():
     assert np.mean(np.abs(out[0][1] - out[1][1]) > 0.5e-3) < 2e-2 and np.mean(np.abs(out[0][2] - out[1][2]) > 0.5e-3) < 2e-2
 
 
+def test_concurrent_streams_match_single_stream():
+    """The step issues independent work on concurrent streams (D's four branches, each layer's weight-gradient chain, fevalG's
+    generator forward; cg_set_concurrency).  Whatever the interleaving, results must equal the single-stream program order:
+    same kernels on the same operands, so only the bilinear scatter's atomic order may differ.  Repeated to give a race a
+    chance to show; B = 16 keeps several CTAs per kernel in flight."""
+    L = lib.load()
+    Cc, B = 3, 16
+    rng = np.random.default_rng(31)
+    x = rng.uniform(0, 1, (B, Cc, 32, 32)).astype(np.float32)
+    z = rng.uniform(-1, 1, (B, 100)).astype(np.float32)
+    go = rng.standard_normal(B).astype(np.float32)
+    gimg = rng.standard_normal((B, Cc, 32, 32)).astype(np.float32)
+    masks = po.make_D_masks(B, rng)
+    ref = None
+    try:
+        for rep, mode in enumerate((0, 1, 1, 1)):
+            lib.check(L.cg_set_concurrency(mode))
+            d = models.create_D((Cc, 32, 32), True, seed=2); g = models.create_G((Cc, 32, 32), 100, seed=1)
+            d.training(); d.set_masks(masks, B, 1)
+            out = d.forward(x).copy(); d.zeroGradParameters(); gx = d.backward(x, go).copy(); gD = d.get_grads()
+            img = g.forward(z).copy(); g.zeroGradParameters(); gz = g.backward(z, gimg).copy(); gG = g.get_grads()
+            cur = (out, gx, gD, img, gz, gG)
+            if ref is None: ref = cur
+            else:
+                for name, a, b in zip(("D out", "D gradInput", "D grads", "G out", "G gradInput", "G grads"), cur, ref):
+                    assert rel(a, b) < 2e-5, (rep, name, rel(a, b))
+        # and the fused step: three steps from the same state, eager, with and without concurrency
+        steps = [(_closure_inputs(rng, Cc, 8)) for _ in range(3)]
+        rec = {}
+        lib.check(L.cg_set_graph_mode(0))
+        for mode in (0, 1):
+            lib.check(L.cg_set_concurrency(mode))
+            g = models.create_G((Cc, 32, 32), 100, seed=1); d = models.create_D((Cc, 32, 32), True, seed=2)
+            t = adversarial.Trainer(g, d)
+            ls = [t.step(lib.default_cfg(8), real[None], zD[None], zG[None]) for real, zD, zG, _, _ in steps]
+            rec[mode] = ([(float(a[0]), float(b[0])) for a, b, _ in ls], g.get_params(), d.get_params())
+        assert abs(rec[0][0][0][0] - rec[1][0][0][0]) < 1e-5 and abs(rec[0][0][0][1] - rec[1][0][0][1]) < 1e-4
+        for i in range(3):
+            assert abs(rec[0][0][i][0] - rec[1][0][i][0]) < 5e-3 and abs(rec[0][0][i][1] - rec[1][0][i][1]) < 5e-3
+        assert np.mean(np.abs(rec[0][1] - rec[1][1]) > 0.5e-3) < 2e-2 and np.mean(np.abs(rec[0][2] - rec[1][2]) > 0.5e-3) < 2e-2
+    finally:
+        lib.check(L.cg_set_concurrency(1)); lib.check(L.cg_set_graph_mode(1))
+
+
 def test_dead_grad_elimination_is_unobservable():
     """Inside fevalG the reference's MODEL_D:backward also accumulates D's parameter gradients, which the next fevalD zeroes
     unread (adversarial.lua:193 vs :78).  cg_train_step skips that accumulation by default (cg_set_dead_grad_elim).  The input-

@@ -517,6 +517,39 @@ def test_graph_replay_matches_eager():
     assert np.mean(np.abs(out[0][1] - out[1][1]) > 0.5e-3) < 2e-2 and np.mean(np.abs(out[0][2] - out[1][2]) > 0.5e-3) < 2e-2
 
 
+def test_sampler_path_matches_oracle():
+    """sample.lua's path -- G and D in evaluate() mode (sample.lua:211,216), images created in chunks of
+    OPT.batchSize with a ragged tail (nn_utils.lua:45-69), D's predictions sorted (nn_utils.lua:89-117).  The oracle runs the
+    same chunks; G's running statistics are first moved off their initial values by two training-mode forwards on both sides."""
+    from catgen import nn_utils
+    Cc, N, bs = 3, 20, 8
+    rng = np.random.default_rng(41)
+    og, od = po.Model(po.G32UPC, Cc, 100, seed=5), po.Model(po.D32_ST3, Cc, 100, seed=6)
+    g = models.create_G((Cc, 32, 32), 100); d = models.create_D((Cc, 32, 32), True)
+    g.set_params(og.params); d.set_params(od.params)
+    for _ in range(2):
+        zw = nn_utils.createNoiseInputs(16, 100, rng)
+        g.forward(zw); og.G_forward(zw, train=True)
+    assert rel(g.get_bn_running(), og.bn_running) < 5e-3
+    nn_utils.switchToEvaluationMode(g, d)
+    z = nn_utils.createNoiseInputs(N, 100, rng)
+    images = nn_utils.createImagesFromNoise(g, z, bs)
+    assert images.shape == (N, Cc, 32, 32) and len(nn_utils.createImagesFromNoise(g, z, bs, outputAsList=True)) == N
+    ref = np.concatenate([og.G_forward(z[s:s + bs], train=False) for s in range(0, N, bs)])
+    assert np.abs(images - ref).max() < 1e-3                      # north_star pixel tolerance
+    assert rel(g.get_bn_running(), og.bn_running) < 5e-3            # evaluate() must not touch the running statistics
+    best, preds = nn_utils.sortImagesByPrediction(d, images, False, 6, bs)
+    worst, wpreds = nn_utils.sortImagesByPrediction(d, images, True, 64, bs)
+    ref_pred = np.concatenate([od.D_forward(ref[s:s + bs], None)[0] for s in range(0, N, bs)])
+    assert len(best) == 6 and len(worst) == N
+    assert np.abs(np.array(preds) - np.sort(ref_pred)[::-1][:6]).max() < 1e-3
+    assert np.abs(np.array(wpreds) - np.sort(ref_pred)).max() < 1e-3
+    assert all(a >= b for a, b in zip(preds, preds[1:])) and all(a <= b for a, b in zip(wpreds, wpreds[1:]))
+    top = int(np.argmax(np.concatenate([d.forward(images[s0:s0 + bs])[:, 0] for s0 in range(0, N, bs)])))
+    assert np.array_equal(best[0], images[top])
+    nn_utils.switchToTrainingMode(g, d)
+
+
 def test_concurrent_streams_match_single_stream():
     """The step issues independent work on concurrent streams (D's four branches, each layer's weight-gradient chain, fevalG's
     generator forward; cg_set_concurrency).  Whatever the interleaving, results must equal the single-stream program order:

@@ -863,6 +863,12 @@ void og_G_forward(og_model* g, const float* z, int B, float* out, int train) {
   memcpy(out, cur, sizeof(float) * (long)B * g->C * 32 * 32);
 }
 
+/* test/diagnostic access to G's saved forward tensors of stage i (valid until the next forward): 0 conv output, 1 BN output, 2 activation */
+const float* og_G_saved(const og_model* g, int stage, int which) {
+  if (stage < 0 || stage >= g->nst) return 0;
+  return which == 0 ? g->sconv[stage] : which == 1 ? g->sbn[stage] : g->sact[stage];
+}
+
 void og_G_backward(og_model* g, const float* gout, float* gz) {
   int B = g->B; int h = 32;
   long no = (long)B * g->C * h * h;

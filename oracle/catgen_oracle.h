@@ -10,7 +10,9 @@
  * and its numerics live in un-vendored luarocks (nn, cudnn, stn, optim) that
  * cannot run in this environment.  The semantics below
  * are restated from the reference call sites and SURVEY.md Appendix A and are
- * cross-checked numerically against PyTorch-CPU autograd (tests/test_oracle_vs_torch.py).
+ * cross-checked numerically against PyTorch-CPU autograd (tests/test_oracle_vs_torch.py) and,
+ * compiled in float64 (OG_F64 below), reproduce that restatement's float64 golden vectors
+ * (tests/golden) to 4e-12 on G and 1e-6 on D (tests/test_golden.py).
  *
  * All tensors are contiguous fp32, Torch7 layout (NCHW, weights [Cout,Cin,kH,kW],
  * Linear [out,in]).  Convolutions: stride 1, pad (k-1)/2 (every call site in
@@ -18,6 +20,26 @@
  */
 #ifndef CATGEN_ORACLE_H
 #define CATGEN_ORACLE_H
+#ifdef OG_F64
+/* libcatgen_oracle_f64.so: THE SAME SOURCE with every `float` widened to double (storage, arithmetic, entry points).  Two fp32
+ * implementations of these networks disagree by ~1e-3 of max|gradient| whenever one PReLU / max-pool decision lands on the
+ * other side of zero (one element of 524288 did in tests/golden/G32upc_rgb_b4); in float64 that noise is gone and the oracle's
+ * SEMANTICS can be compared with the float64 PyTorch restatement to ~1e-7 (tests/test_golden.py).  Model-level entry points only:
+ * og_step_cfg changes layout in this build and the trainer is not bound from Python.
+ * The system headers must be seen before `float` is redefined. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#define float double
+#define floorf floor
+#define sqrtf sqrt
+#define fabsf fabs
+#define expf exp
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -110,6 +132,8 @@ long      og_D_mask_floats(int B);
 void og_G_forward(og_model* g, const float* z, int B, float* out, int train);
 /* gout [B,C,32,32]; accumulates param grads; gz may be NULL */
 void og_G_backward(og_model* g, const float* gout, float* gz);
+/* diagnostic: G's saved forward tensor of a stage (0 conv output, 1 BN output, 2 activation), valid until the next forward */
+const float* og_G_saved(const og_model* g, int stage, int which);
 /* D: x [B,C,32,32] -> out_sig [B], out_pre [B] (either may be NULL) */
 void og_D_forward(og_model* d, const float* x, int B, const float* masks, float* out_sig, float* out_pre);
 /* gout: d loss / d sigmoid-output [B]; gx [B,C,32,32] may be NULL */

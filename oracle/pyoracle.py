@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libcatgen_oracle.so")
+_SO64 = os.path.join(_HERE, "libcatgen_oracle_f64.so")   # the same source with float widened to double (catgen_oracle.h, OG_F64)
 
 G32UP, G32UPC, D32_ST3 = 0, 1, 2
 _fp = C.POINTER(C.c_float)
@@ -19,7 +20,7 @@ _ip = C.POINTER(C.c_int)
 
 def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("catgen_oracle.c", "catgen_oracle.h", "Makefile")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+    if force or not os.path.exists(_SO) or not os.path.exists(_SO64) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -126,6 +127,31 @@ def lib():
     return L
 
 
+_lib64 = None
+
+
+def lib64():
+    """The float64 build: model-level entry points only (og_step_cfg has another layout there and the trainer is not bound)."""
+    global _lib64
+    if _lib64 is not None:
+        return _lib64
+    if not os.path.exists(_SO64):
+        build(force=True)
+    L = C.CDLL(_SO64)
+    i, l, vp, dp = C.c_int, C.c_long, C.c_void_p, C.POINTER(C.c_double)
+
+    def sig(name, res, *args):
+        fn = getattr(L, name); fn.restype = res; fn.argtypes = list(args)
+    sig("og_model_create", vp, i, i, i); sig("og_model_free", None, vp); sig("og_model_nparams", l, vp)
+    sig("og_model_params", dp, vp); sig("og_model_grads", dp, vp); sig("og_model_zero_grads", None, vp)
+    sig("og_D_mask_floats", l, i)
+    sig("og_G_forward", None, vp, dp, i, dp, i); sig("og_G_backward", None, vp, dp, dp)
+    sig("og_D_forward", None, vp, dp, i, dp, dp, dp); sig("og_D_backward", None, vp, dp, dp)
+    L.og_set_threads(min(usable_cpus(), 16))
+    _lib64 = L
+    return L
+
+
 def P(a):
     """float32 C-contiguous ndarray (or None) -> float*"""
     if a is None:
@@ -156,10 +182,14 @@ def _view(ptr, n, owner):
 
 
 class Model:
-    """Oracle G or D with parameters as a flat vector in nn getParameters() order."""
+    """Oracle G or D with parameters as a flat vector in nn getParameters() order.
+    f64=True: the float64 build (parameters start at zero there -- copy them from an fp32 Model; forward/backward only)."""
 
-    def __init__(self, kind, C_img=3, nz=100, seed=None):
-        self.L = lib()
+    def __init__(self, kind, C_img=3, nz=100, seed=None, f64=False):
+        self.f64 = bool(f64)
+        self.L = lib64() if f64 else lib()
+        self.dt = np.float64 if f64 else np.float32
+        assert not (f64 and seed is not None), "initialise an fp32 Model and copy its parameters"
         self.kind, self.C, self.nz = kind, C_img, nz
         self.h = self.L.og_model_create(kind, C_img, nz)
         self.n = self.L.og_model_nparams(self.h)
@@ -182,6 +212,7 @@ class Model:
 
     @property
     def bn_running(self):
+        assert not self.f64
         n = C.c_long()
         p = self.L.og_model_bn_running(self.h, C.byref(n))
         return _view(p, n.value, self) if n.value else np.zeros(0, np.float32)
@@ -189,33 +220,42 @@ class Model:
     def zero_grads(self):
         self.L.og_model_zero_grads(self.h)
 
+    def _a(self, a):
+        return np.ascontiguousarray(a, dtype=self.dt)
+
+    def _p(self, a):
+        if a is None:
+            return None
+        assert a.dtype == self.dt and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.POINTER(C.c_double if self.f64 else C.c_float))
+
     def G_forward(self, z, train=True):
-        z = f32(z)
+        z = self._a(z)
         B = z.shape[0]
-        out = np.empty((B, self.C, 32, 32), np.float32)
-        self.L.og_G_forward(self.h, P(z), B, P(out), 1 if train else 0)
+        out = np.empty((B, self.C, 32, 32), self.dt)
+        self.L.og_G_forward(self.h, self._p(z), B, self._p(out), 1 if train else 0)
         return out
 
     def G_backward(self, gout):
-        gout = f32(gout)
-        gz = np.empty((gout.shape[0], self.nz), np.float32)
-        self.L.og_G_backward(self.h, P(gout), P(gz))
+        gout = self._a(gout)
+        gz = np.empty((gout.shape[0], self.nz), self.dt)
+        self.L.og_G_backward(self.h, self._p(gout), self._p(gz))
         return gz
 
     def D_forward(self, x, masks=None):
-        x = f32(x)
+        x = self._a(x)
         B = x.shape[0]
-        sig, pre = np.empty(B, np.float32), np.empty(B, np.float32)
+        sig, pre = np.empty(B, self.dt), np.empty(B, self.dt)
         if masks is not None:
-            masks = f32(masks)
+            masks = self._a(masks)
             assert masks.size == self.L.og_D_mask_floats(B)
-        self.L.og_D_forward(self.h, P(x), B, P(masks), P(sig), P(pre))
+        self.L.og_D_forward(self.h, self._p(x), B, self._p(masks), self._p(sig), self._p(pre))
         return sig, pre
 
     def D_backward(self, gout):
-        gout = f32(gout)
-        gx = np.empty((gout.shape[0], self.C, 32, 32), np.float32)
-        self.L.og_D_backward(self.h, P(gout), P(gx))
+        gout = self._a(gout)
+        gx = np.empty((gout.shape[0], self.C, 32, 32), self.dt)
+        self.L.og_D_backward(self.h, self._p(gout), self._p(gx))
         return gx
 
 

@@ -3,16 +3,17 @@ STATUS: WRITTEN, NOT EXECUTED (see catgen_ffi.lua).  Same guard, constructor and
 (LeakyReLU.lua:2-31); updateGradInput gives gradOutput where input >= 0, INCLUDING input == 0 (:21-31). ]]
 if nn.LeakyReLU then return end
 local cg = require("catgen_ffi")
-local LeakyReLU, parent = torch.class('nn.LeakyReLU', 'nn.Module')
-function LeakyReLU:__init(negative_scale)
-   parent.__init(self); self.negative_scale = negative_scale or 0.333
+local M, base = torch.class('nn.LeakyReLU', 'nn.Module')   -- same class name: the reference's models.lua instantiates nn.LeakyReLU
+function M:__init(slope)
+   base.__init(self)
+   self.negative_scale = slope or 0.333   -- field name kept: checkpoints of the reference carry it
 end
-function LeakyReLU:updateOutput(input)
+function M:updateOutput(input)
    cg.init(); input = input:contiguous(); self.output:resizeAs(input)
    cg.check(cg.lib.cg_leakyrelu_fwd(cg.ptr(input), self.negative_scale, cg.ptr(self.output), input:nElement()))
    return self.output
 end
-function LeakyReLU:updateGradInput(input, gradOutput)
+function M:updateGradInput(input, gradOutput)
    input = input:contiguous(); gradOutput = gradOutput:contiguous(); self.gradInput:resizeAs(gradOutput)
    cg.check(cg.lib.cg_leakyrelu_bwd(cg.ptr(input), cg.ptr(gradOutput), self.negative_scale, cg.ptr(self.gradInput), input:nElement()))
    return self.gradInput

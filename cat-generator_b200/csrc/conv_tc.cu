@@ -12,10 +12,18 @@
 //  * B operand = weights, pre-packed on the device into the exact shared-memory image of one
 //      (64-channel block, tap) slice [c][co][16 B] and streamed by ONE cp.async.bulk per slice through a ring.
 //  * accumulators in TMEM (fp32), read back with tcgen05.ld (lane = pixel, column = co).
-//  * operands: fp16 (kind::f16) for fprop, tf32 (kind::tf32) for dgrad -- tools/precision_study.py and
-//    tools/backward_precision_study.py: bf16 and unscaled fp16 gradients miss the parity targets.
-// Warp roles (160 threads): warp 4 = weight-slice producer (1 lane) ; warp 5? no -- see kernel: warps 0-3 are
-// the epilogue (they own the four TMEM lane quarters), warp 4 streams weights, warp 5 loads patches, warp 6 issues MMAs.
+//  * operands: fp16 (kind::f16) everywhere; gradient-valued operands are multiplied by a per-tensor power of two first
+//    (tools/precision_study.py, tools/backward_precision_study.py: bf16 and unscaled fp16 gradients miss the parity
+//    targets, scaled fp16 equals tf32).  The tf32 instantiation stays behind CATGEN_DGRAD_TF32=1.
+// Warp roles (256 threads): warps 0-3 = epilogue (they own the four TMEM lane quarters; stores go through a shared-memory
+// tile so that they leave as whole 128-byte lines), warp 4 streams weight slices, warp 5 loads patches (one tiled TMA per
+// channel block), warps 6 and 7 issue the MMAs of tile 0 / tile 1 of the CTA (one thread retires an MMA per ~84 cycles,
+// two reach the pipe's 64: tools/tc_rate.cu).
+// File layout: pack kernels (activations, weight slices, the fused G producer, the one-launch model repack) ; k_conv_tc
+// (fprop + dgrad) ; host planning / launch ; gradient-operand statistics and packing ; k_wgrad_tc ; conv_bwd_tc (one packed
+// gradient operand feeds dgrad on the issuing stream and wgrad on its side stream).
+// Experiment knobs (not for production): CATGEN_TC_RING (cap the weight ring), CATGEN_TC_ROT (per-CTA tap rotation),
+// CATGEN_TC_DBG=1|2 (per-CTA clock64 timeline to stderr; 2 also drops the epilogue stores).
 #include <unordered_map>
 #include "ops.cuh"
 #include <cuda.h>

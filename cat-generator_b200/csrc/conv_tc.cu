@@ -549,9 +549,232 @@ bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
   return *CB != 0;
 }
 
+// ====================================================================================================================
+// EXPERIMENT FOR ROUND 2 -- WRITTEN WITHOUT A GPU, NEVER RUN, OFF BY DEFAULT (CATGEN_TC_TL4=1 selects it for fp16 runs).
+// Four tiles per CTA instead of two, so that every weight slice fetched from L2 feeds 512 pixels instead of 256.
+// Why: DESIGN.md section 4.1 -- with two 128-wide tiles a CTA has to take in 18.8 KB per 512 cycles of MMA work (36.7 B/cycle/SM)
+// and gets 23.5; the main loop waits a quarter of its time for weights whatever the ring depth.  With four tiles (all 512 TMEM
+// columns at N = 128) and 32-channel blocks (so that 2 x 4 patch buffers still fit) the same 512 cycles need 8 KB of weights +
+// 2.5 KB of patches = 20.5 B/cycle/SM.  If the hypothesis is right, conv3 fprop goes from ~235 us towards ~150 us; if the time
+// does not move, the hypothesis is wrong and the CTA-pair kernel (tools/tc_pair_probe.cu) is not the fix either.
+// Same operands, barriers and epilogue as k_conv_tc<2>; differences: TL = 4, slices of 32 channels (two MMAs per tile and
+// slice), issuer warp 6 owns tiles 0-1 and warp 7 tiles 2-3.  Parity: run tests/test_gpu_parity.py with CATGEN_TC_TL4=1.
+struct Tc4Params {
+  const uint8_t *xq, *wq; const float *bias, *scale2; float* y;
+  int N, H, W, Ci, Co, Cor, k, p, Hq, Wq, ncb, tiles_x, tiles_y, NB, S, ntiles;
+  uint32_t patch_bytes, slice_bytes;
+};
+__global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int Cop, int kk) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 4); t /= 4; int tap = (int)(t % kk); int cb = (int)(t / kk);
+    int ci0 = cb * 32 + c * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (co < Co && ci0 + j < Ci) ? Wp[((long)tap * Ci + ci0 + j) * Co + co] : 0.f;
+    uint4 out; uint32_t* o = &out.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); o[j] = *reinterpret_cast<uint32_t*>(&h); }
+    reinterpret_cast<uint4*>(Wq)[i] = out;
+  }
+}
+__global__ void __launch_bounds__(256, 1) k_conv_tc4(Tc4Params P, const __grid_constant__ CUtensorMap tmx) {
+  constexpr int TLX = 4, PLX = 4;                           // tiles per CTA; 16-byte channel planes per 32-channel block / slice
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[16], bar_wempty[16], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* patch0 = smem;                                    // patch buffers [2][TLX]
+  uint8_t* wring = smem + 2 * (size_t)TLX * P.patch_bytes;   // S weight slices
+  const int tile0 = blockIdx.x * TLX;
+  const int ntl = (P.ntiles - tile0) < TLX ? (P.ntiles - tile0) : TLX;
+  auto tile_xy = [&](int tl, int& n, int& y0, int& x0) {
+    int t = tile0 + tl; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
+  };
+  const int co0 = blockIdx.y * P.NB;
+  const int Hp = 16 + 2 * P.p, Wp = 8 + 2 * P.p;
+  const uint32_t plane_bytes = (uint32_t)Hp * Wp * 16;
+  const int kk = P.k * P.k;
+  const int nslices = P.ncb * kk;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 2); }
+    for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
+    mbar_init(&bar_acc, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  int ncols = 32; while (ncols < TLX * P.NB) ncols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 4) {
+    if (lane == 0) {   // weight slices [slice][c 0..3][Co][16 B]
+      int st = 0; uint32_t ph = 0;
+      for (int s = 0; s < nslices; ++s, st = (st + 1 == P.S) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
+        mbar_wait(&bar_wempty[st], ph ^ 1);
+        mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
+        uint8_t* dst = wring + (size_t)st * P.slice_bytes;
+        const uint8_t* src = P.wq + (size_t)s * PLX * P.Co * 16;
+        if (P.NB == P.Co) bulk_g2s(dst, src, P.slice_bytes, &bar_wfull[st]);
+        else for (int c = 0; c < PLX; ++c) bulk_g2s(dst + (size_t)c * P.NB * 16, src + ((size_t)c * P.Co + co0) * 16, P.NB * 16, &bar_wfull[st]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {   // patches: one tiled TMA per tile and 32-channel block
+      for (int cb = 0; cb < P.ncb; ++cb) {
+        int buf = cb & 1; uint32_t ph = (cb >> 1) & 1;
+        mbar_wait(&bar_pempty[buf], ph ^ 1);
+        mbar_expect_tx(&bar_pfull[buf], (uint32_t)ntl * P.patch_bytes);
+        for (int tl = 0; tl < ntl; ++tl) {
+          int n, y0, x0; tile_xy(tl, n, y0, x0);
+          tma_patch_4d(patch0 + (size_t)(buf * TLX + tl) * P.patch_bytes, &tmx, x0 * 8, y0, cb * PLX, n, &bar_pfull[buf]);
+        }
+      }
+    }
+  } else if (warp == 6 || warp == 7) {
+    if (lane == 0) {   // two issuers, two tiles each; per slice and tile: two MMAs (32 channels = 2 x K 16)
+      const int me = warp - 6;
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t b_lbo = (uint32_t)P.NB * 16;
+      const uint32_t a_hi = desc_hi((uint32_t)Wp * 16), b_hi = desc_hi(128);
+      const uint32_t plane16 = plane_bytes >> 4, patch16 = P.patch_bytes >> 4, slice16 = P.slice_bytes >> 4;
+      const uint32_t a_kstep = 2 * plane16, b_kstep = 2 * (b_lbo >> 4);
+      const uint32_t w_lo0 = desc_lo(smem_u32(wring), b_lbo);
+      const int S = P.S, k = P.k, NB = P.NB;
+      uint32_t st = 0, wph = 0, acc0 = 0;
+      for (int cb = 0; cb < P.ncb; ++cb) {
+        const int buf = cb & 1;
+        mbar_wait(&bar_pfull[buf], (cb >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t p_lo0 = desc_lo(smem_u32(patch0 + (size_t)(buf * TLX) * P.patch_bytes), plane_bytes);
+        uint32_t row_lo = p_lo0;
+        for (int ky = 0; ky < k; ++ky, row_lo += (uint32_t)Wp) {
+          for (int kx = 0; kx < k; ++kx) {
+            const uint32_t a_lo = row_lo + (uint32_t)kx;
+            mbar_wait(&bar_wfull[st], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t w_lo = w_lo0 + st * slice16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int tl = 2 * me + j;
+              if (tl < ntl) {
+                const uint32_t at = a_lo + (uint32_t)tl * patch16, tm = tmem + (uint32_t)(tl * NB);
+                umma<2>(tm, desc64(at, a_hi), desc64(w_lo, b_hi), idesc, acc0);
+                umma<2>(tm, desc64(at + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+              }
+            }
+            acc0 = 1u;
+            umma_commit(&bar_wempty[st]);
+            if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
+          }
+        }
+        umma_commit(&bar_pempty[buf]);
+      }
+      umma_commit(&bar_acc);
+    }
+  }
+
+  if (warp < 4) {   // epilogue as in k_conv_tc: staged through shared memory for full-width blocks, per-lane stores otherwise
+    mbar_wait(&bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const int m = warp * 32 + lane;
+    const bool vec = (P.Cor & 3) == 0;
+    const float inv = P.scale2 ? P.scale2[1] : 1.f;
+    float* stage = reinterpret_cast<float*>(patch0) + warp * (32 * 36);
+    const bool wide = vec && (P.NB & 31) == 0;
+    for (int tl = 0; tl < ntl; ++tl) {
+      int n, y0, x0; tile_xy(tl, n, y0, x0);
+      for (int c0 = 0; c0 < P.NB; c0 += 16) {
+        uint32_t v[16];
+        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        if (wide && co0 + c0 + 16 <= P.Cor) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co0 + c0 + j] : 0.f);
+            o.y = __uint_as_float(v[j + 1]) * inv + (P.bias ? P.bias[co0 + c0 + j + 1] : 0.f);
+            o.z = __uint_as_float(v[j + 2]) * inv + (P.bias ? P.bias[co0 + c0 + j + 2] : 0.f);
+            o.w = __uint_as_float(v[j + 3]) * inv + (P.bias ? P.bias[co0 + c0 + j + 3] : 0.f);
+            *reinterpret_cast<float4*>(stage + lane * 20 + j) = o;          // 16 + 4 pad floats per pixel row
+          }
+          __syncwarp();
+          const int q = (lane & 3) * 4;                                       // 4 lanes per pixel (64 bytes), 8 pixels per store
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pl = i * 8 + (lane >> 2), mm = warp * 32 + pl;
+            const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+            float4 o = *reinterpret_cast<const float4*>(stage + pl * 20 + q);
+            if (oy < P.H && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q) = o;
+          }
+          __syncwarp();
+        } else {
+          const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+          if (oy < P.H && ox < P.W) {
+            float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+            for (int j = 0; j < 16; ++j) { int co = co0 + c0 + j; if (co < P.Cor) out[c0 + j] = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co] : 0.f); }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+}
+static int conv_tc4_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
+                        const uint8_t* xq_prepacked) {
+  const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // same operand padding as conv_tc_run<2>: the packed activations are shared
+  const int p = (k - 1) / 2, kk = k * k;
+  const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
+  int NB = Co > 128 ? 128 : Co; while (NB >= 16 && Co % NB) NB -= 16;       // four accumulators of NB columns must fit 512 TMEM columns
+  if (NB < 16) return CG_ERR_UNSUPPORTED;
+  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * NB * 16;
+  if (8 * patch_bytes + 3 * slice_bytes > 216 * 1024) return CG_ERR_UNSUPPORTED;
+  int S = (int)((216 * 1024 - 8 * patch_bytes) / slice_bytes); if (S > 16) S = 16;
+  const int ntiles = N * (W / 8) * ((H + 15) / 16);
+  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * 2;
+  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255)) + wq_bytes + 512);
+  if (!ws) return CG_ERR_CUDA;
+  const uint8_t* xq = xq_prepacked ? xq_prepacked : ws;
+  uint8_t* wq = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
+  long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
+  if (!xq_prepacked) CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2);
+  CG_LAUNCH(k_pack_wslices32, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk);
+  Tc4Params P{};
+  P.xq = xq; P.wq = wq; P.bias = bias; P.scale2 = scale2; P.y = y;
+  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
+  P.ncb = Ci / 32; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S; P.ntiles = ntiles;
+  P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
+  size_t smem = 8 * patch_bytes + (size_t)S * slice_bytes;
+  static bool attr_done = false;
+  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
+  dim3 grid((ntiles + 3) / 4, Co / NB);
+  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;
+  ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
+  CUtensorMap tmx;
+  CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
+  CG_LAUNCH(k_conv_tc4, grid, 256, smem, P, tmx);
+  return CG_OK;
+}
+// ====================================================================================================================
+
 template <int ES>
 static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
                        const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
+  if (ES == 2) {   // round-2 experiment, never run yet (see k_conv_tc4)
+    static const bool tl4 = getenv("CATGEN_TC_TL4") != nullptr;
+    if (tl4) { int s4 = conv_tc4_run(x, Wp, bias, y, N, H, W, Cir, Cor, k, scale2, xq_prepacked); if (s4 != CG_ERR_UNSUPPORTED) return s4; }
+  }
   constexpr int PER = 16 / ES, KB = 128 / ES;
   const int Ci = ((Cir + KB - 1) / KB) * KB, Co = ((Cor + 15) / 16) * 16;   // padded sizes the kernel iterates over
   const int p = (k - 1) / 2, kk = k * k;

@@ -550,7 +550,9 @@ bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
 }
 
 // ====================================================================================================================
-// EXPERIMENT FOR ROUND 2 -- WRITTEN WITHOUT A GPU, NEVER RUN, OFF BY DEFAULT (CATGEN_TC_TL4=1 selects it for fp16 runs).
+// EXPERIMENT FOR ROUND 2 -- OFF BY DEFAULT (CATGEN_TC_TL4=1 selects it for fp16 runs).  Written without a GPU; run ONCE at the very end of
+// round 1: the op-level conv parity tests pass with it and G conv3 fprop took 194 us instead of 234, dgrad 206 instead of 227
+// (profiles/r01_conv3_tl4_experiment.txt).  The model-level suite has not been run with it, hence not the default yet.
 // Four tiles per CTA instead of two, so that every weight slice fetched from L2 feeds 512 pixels instead of 256.
 // Why: DESIGN.md section 4.1 -- with two 128-wide tiles a CTA has to take in 18.8 KB per 512 cycles of MMA work (36.7 B/cycle/SM)
 // and gets 23.5; the main loop waits a quarter of its time for weights whatever the ring depth.  With four tiles (all 512 TMEM
@@ -771,7 +773,7 @@ static int conv_tc4_run(const float* x, const float* Wp, const float* bias, floa
 template <int ES>
 static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
                        const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
-  if (ES == 2) {   // round-2 experiment, never run yet (see k_conv_tc4)
+  if (ES == 2) {   // round-2 experiment (see k_conv_tc4)
     static const bool tl4 = getenv("CATGEN_TC_TL4") != nullptr;
     if (tl4) { int s4 = conv_tc4_run(x, Wp, bias, y, N, H, W, Cir, Cor, k, scale2, xq_prepacked); if (s4 != CG_ERR_UNSUPPORTED) return s4; }
   }

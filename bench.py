@@ -79,47 +79,102 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def sample_batch(cores):
-    """Images per CPU step: the oracle parallelises over samples, so the sample must be >= the thread count to use
-    all host threads, and small enough that one step stays within ~10-30 s."""
-    return 128 if cores >= 32 else (64 if cores >= 16 else 16)
+def _host_inputs(B, rng, d=1, g=1, C=3):
+    real = rng.uniform(0, 1, (d, B // 2, C, 32, 32)).astype(np.float32)
+    zD = rng.uniform(-1, 1, (d, B // 2, 100)).astype(np.float32)
+    zG = rng.uniform(-1, 1, (g, B, 100)).astype(np.float32)
+    return real, zD, zG
 
 
-def cpu_baseline(B_sample, threads, steps=1, warm=0):
-    """The oracle port of the reference's CPU path (no Torch7/LuaJIT exists in this image) timed on the host."""
+def cpu_oracle_port(B, threads, steps=1):
+    """The C oracle port of the reference's Torch7 nn CPU path (per-sample im2col + hand-rolled SGEMM, OpenMP)."""
     from oracle import pyoracle as po
     L = po.lib()
     L.og_set_threads(threads)
     rng = np.random.default_rng(1)
     G, D = po.Model(po.G32UPC, 3, 100, seed=1), po.Model(po.D32_ST3, 3, 100, seed=2)
     T = po.Trainer(G, D)
-    cfg = po.default_cfg(B_sample)
+    cfg = po.default_cfg(B)
     times = []
-    for s in range(warm + steps):
-        real = rng.uniform(0, 1, (1, B_sample // 2, 3, 32, 32)).astype(np.float32)
-        zD = rng.uniform(-1, 1, (1, B_sample // 2, 100)).astype(np.float32)
-        zG = rng.uniform(-1, 1, (1, B_sample, 100)).astype(np.float32)
-        masks = np.stack([po.make_D_masks(B_sample, rng) for _ in range(2)])
+    for s in range(steps):
+        real, zD, zG = _host_inputs(B, rng)
+        masks = np.stack([po.make_D_masks(B, rng) for _ in range(2)])
         t0 = time.perf_counter()
         T.step(cfg, real, zD, zG, masks)
-        if s >= warm:
-            times.append(time.perf_counter() - t0)
+        times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return B_sample / dt, dt
+    return B / dt, dt
+
+
+class _TorchCpu:
+    """BASELINE.md section 3 "B-mkl": the same step with PyTorch CPU ops (oneDNN/MKL) + autograd, the stand-in for
+    "Torch7 nn + optimised BLAS" (oracle/torch_step.py).  kind/C/B/d select the BASELINE config."""
+
+    def __init__(self, threads, kind="G32UPC", C=3, B=128, d=1):
+        import torch
+        from oracle import pyoracle as po, torch_step as ts
+        torch.set_num_threads(threads)
+        self.ts, self.po, self.kind, self.C, self.B, self.d = ts, po, kind, C, B, d
+        og = po.Model(po.G32UPC if kind == "G32UPC" else po.G32UP, C, 100, seed=1)
+        od = po.Model(po.D32_ST3, C, 100, seed=2)
+        self.G, self.D = ts.Net(np.array(og.params)), ts.Net(np.array(od.params))
+        self.cfg = po.default_cfg(B, d, 1)
+        self.rng = np.random.default_rng(1)
+
+    def step(self, B=None):
+        B = B or self.B
+        cfg = self.po.default_cfg(B, self.d, 1)
+        real, zD, zG = _host_inputs(B, self.rng, self.d, 1, self.C)
+        masks = np.stack([self.po.make_D_masks(B, self.rng) for _ in range(self.d + 1)])
+        t0 = time.perf_counter()
+        self.ts.train_step(self.G, self.D, cfg, real, zD, zG, masks, self.kind, self.C)
+        return time.perf_counter() - t0
+
+
+def cpu_info():
+    model = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    return {"nproc": os.cpu_count(), "model": model}
 
 
 def run_reference(args, rank, out_stream):
+    """--impl reference: the reference's CPU path on the box's host cores, same config as the GPU arm (G32up-c + D32_st3, RGB,
+    batch 128 per step), EXACTLY args.steps timed steps after args.warmup untimed ones.  Torch7 cannot run here (BASELINE.md
+    section 2): the timed implementation is the faster of our two CPU restatements, PyTorch-CPU (oneDNN/MKL) -- the C oracle port
+    is timed for one step beside it."""
     if rank != 0:
         return
     from oracle import pyoracle as _po
     cores = _po.usable_cpus()
-    Bs = sample_batch(cores)
-    v, dt = cpu_baseline(Bs, cores, steps=max(1, min(args.steps, 3)), warm=min(args.warmup, 1))
-    sample = "G32up-c+D32_st3 RGB step at batch %d (the B=128 workload cut to %d images per step), oracle port, %d OpenMP threads" % (Bs, Bs, cores)
+    B = args.batch
+    T = _TorchCpu(cores, B=B)
+    for _ in range(args.warmup):
+        T.step()
+    times = [T.step() for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    v = B / dt
+    ov, odt = cpu_oracle_port(B, cores, steps=1)
+    # BASELINE configs[0] (c1): G32up grayscale, batch 16, one adversarial.train epoch of N_epoch=1000 = 125 steps; bounded sample of 10 steps
+    c1 = {}
+    for th in sorted({min(4, cores), cores}):
+        T1 = _TorchCpu(th, kind="G32UP", C=1, B=16)
+        T1.step()
+        t1 = float(np.mean([T1.step() for _ in range(10)]))
+        c1["threads_%d" % th] = {"s_per_step": t1, "s_per_epoch_extrapolated": t1 * 125, "ms_per_sample": 1000 * t1 * 125 / 1000, "images_per_s": 16 / t1}
+    sample = ("%d timed adversarial.train loop bodies of G32up-c + D32_st3, RGB, batch %d (the GPU arm's config), PyTorch-CPU fp32 restatement "
+              "(oracle/torch_step.py), %d threads" % (args.steps, B, cores))
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "G32up-c + D32_st3, RGB 3x32x32, adversarial.train loop body, CPU", "batch_per_step": Bs},
-           "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": "BASELINE configs[1]: G32up-c + D32_st3, RGB 3x32x32, batch %d, D_iterations=1, G_iterations=1, CPU" % B, "global_batch": B},
+           "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample, "host": cpu_info(),
+                            "oracle_port": {"value": ov, "unit": "images/s", "cores": cores, "s_per_step": odt,
+                                            "what": "C restatement of the Torch7 nn CPU algorithms (oracle/catgen_oracle.c), one step at batch %d" % B},
+                            "c1_G32up_gray_b16_epoch": c1},
            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     out_stream.write(json.dumps(out) + "\n"); out_stream.flush()
 
@@ -158,7 +213,7 @@ def main():
         faulthandler.cancel_dump_traceback_later()
         faulthandler.dump_traceback_later(45, exit=False)
     # hard watchdog: a deadlocked collective must end as a failed run with a message, never as a hang the driver has to kill
-    limit = float(os.environ.get("CATGEN_BENCH_LIMIT_S", "900"))
+    limit = float(os.environ.get("CATGEN_BENCH_LIMIT_S", "300"))   # well inside the driver's per-run limit, so a hang leaves a stack
     def _watchdog():
         time.sleep(limit)
         sys.stderr.write("[bench rank %d] watchdog: not finished after %.0f s, aborting\n" % (rank, limit)); sys.stderr.flush()
@@ -171,20 +226,24 @@ def main():
     lib.init(local)
     dist = None
     if world > 1:
-        import torch
+        # Control plane (rendezvous, barrier, max-over-ranks) = torch.distributed over gloo; data plane = ONE NCCL communicator, the
+        # library's own (cg_dist_init), carrying the gradient all-reduces over NVLink.  Round 1 kept a second NCCL communicator
+        # (torch's) in the same process and the 8-GPU run of the driver hung with rank 0 spinning in a collective.
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        stage("torch.distributed init (nccl)")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        from catgen import dist as cgd
+        stage("torch.distributed init (gloo control plane)")
+        dist.init_process_group("gloo")
+        raw = None
         if rank == 0:
             raw = C.create_string_buffer(128)
             lib.check(L.cg_dist_unique_id(raw))
-            idbuf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+            raw = raw.raw
         stage("broadcast ncclUniqueId")
-        dist.broadcast(idbuf, 0)
-        stage("cg_dist_init (ncclCommInitRank)")
-        lib.check(L.cg_dist_init(rank, world, bytes(idbuf.cpu().numpy().tobytes())))
+        uid = cgd.broadcast_bytes(raw, 0, dist)
+        stage("cg_dist_init (ncclCommInitRank, %d ranks)" % world)
+        lib.check(L.cg_dist_init(rank, world, uid))
+        if os.environ.get("CATGEN_SYNC_BN"):
+            lib.check(L.cg_dist_set_sync_bn(1))
 
     stage("creating models")
     B, Cc, nz = args.batch, 3, 100
@@ -197,11 +256,12 @@ def main():
     nsteps = K + W
 
     def barrier():
-        lib.check(L.cg_sync())
+        lib.check(L.cg_sync())          # cudaStreamSynchronize of the library's stream: every kernel and collective of this rank is done
         if dist is not None:
             dist.barrier()
-            import torch
-            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        return cgd.max_over_ranks(v, dist) if dist is not None else float(v)
 
     # ---- device-resident synthetic inputs, distinct per step and per rank (U[0,1) images, U(-1,1) noise)
     n_real, n_zd, n_zg = hB * img, hB * nz, B * nz
@@ -234,10 +294,7 @@ def main():
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     launches = int(L.cg_launch_count())
     clk = clocks.stop() if clocks else None
-    ms_max = ms.value
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms.value], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_max = float(t.item())
+    ms_max = max_over_ranks(ms.value)
     value = world * B * K / (ms_max / 1e3)
     # the same K device-resident steps again WITHOUT the nvidia-smi sampler: e2e (measured unsampled) kept coming out
     # above `value`, and the only thing specific to the region above is the 100 ms NVML polling
@@ -247,26 +304,25 @@ def main():
         dev_step(i, i == W + K - 1)
     ms_u = C.c_float(); lib.check(L.cg_timer_stop(C.byref(ms_u)))
     barrier()
-    ms_u_max = ms_u.value
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_u.value], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_u_max = float(t.item())
+    ms_u_max = max_over_ranks(ms_u.value)
 
     stage("end-to-end region")
     # ---- end to end through the public call with HOST buffers (pinned), H2D + D2H inside the timed region
-    import torch
-    pin = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+    def pin(*shape):
+        """page-locked host buffer from the library (cudaMallocHost) viewed as a float32 ndarray; no torch CUDA context anywhere"""
+        n = int(np.prod(shape))
+        ptr = L.cg_host_alloc(4 * n)
+        assert ptr, "cg_host_alloc failed"
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n,)).reshape(shape), ptr
     rng = np.random.default_rng(7 + rank)
     Ke = K
-    h_real, h_zd, h_zg = pin(Ke, hB, Cc, 32, 32), pin(Ke, hB, nz), pin(Ke, B, nz)
-    h_real.copy_(torch.from_numpy(rng.uniform(0, 1, h_real.shape).astype(np.float32)))
-    h_zd.copy_(torch.from_numpy(rng.uniform(-1, 1, h_zd.shape).astype(np.float32)))
-    h_zg.copy_(torch.from_numpy(rng.uniform(-1, 1, h_zg.shape).astype(np.float32)))
-    h_out = pin(Ke, B + 2)
-    outp = h_out.numpy()
+    (h_real, p_real), (h_zd, p_zd), (h_zg, p_zg) = pin(Ke, hB, Cc, 32, 32), pin(Ke, hB, nz), pin(Ke, B, nz)
+    h_real[...] = rng.uniform(0, 1, h_real.shape); h_zd[...] = rng.uniform(-1, 1, h_zd.shape); h_zg[...] = rng.uniform(-1, 1, h_zg.shape)
+    outp, p_out = pin(Ke, B + 2)
+    outp[...] = np.nan
 
     def host_step(i):
-        lib.check(L.cg_train_step(T.h, C.byref(cfg), h_real[i].data_ptr(), h_zd[i].data_ptr(), h_zg[i].data_ptr(),
+        lib.check(L.cg_train_step(T.h, C.byref(cfg), h_real[i].ctypes.data, h_zd[i].ctypes.data, h_zg[i].ctypes.data,
                                   lib.P(outp[i, B:B + 1]), lib.P(outp[i, B + 1:B + 2]), lib.P(outp[i, :B])))
     for i in range(min(3, Ke)):
         host_step(i)
@@ -276,9 +332,7 @@ def main():
         host_step(i)
     ms_e = C.c_float(); lib.check(L.cg_timer_stop(C.byref(ms_e)))
     barrier()
-    ms_e_max = ms_e.value
-    if dist is not None:
-        t = torch.tensor([ms_e.value], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e_max = float(t.item())
+    ms_e_max = max_over_ranks(ms_e.value)
     e2e = world * B * Ke / (ms_e_max / 1e3)
     h2d = 4 * (n_real + n_zd + n_zg); d2h = 4 * (B + 2)
     assert np.isfinite(outp).all(), "non-finite loss / D output in the end-to-end region"
@@ -288,7 +342,8 @@ def main():
     # of steps every rank must hold bit-identical parameters (different data per rank, one all-reduce per network per update)
     in_sync = None
     if dist is not None:
-        chk = torch.tensor([float(np.sum(G.get_params().astype(np.float64))), float(np.sum(D.get_params().astype(np.float64)))], dtype=torch.float64, device="cuda")
+        import torch
+        chk = torch.tensor([float(np.sum(G.get_params().astype(np.float64))), float(np.sum(D.get_params().astype(np.float64)))], dtype=torch.float64)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool(torch.equal(lo, hi))
@@ -298,19 +353,21 @@ def main():
     kp = min(K, 3)
     # one stream, program order: with the step's concurrent lanes on, an event-bracketed launch also counts the time it
     # shares the SMs with other lanes' kernels, which is not that kernel's duration
+    # EVERY rank takes the SAME path through these steps -- profiling on (hence eager, never a graph capture) and one stream
+    # everywhere: each step contains the gradient all-reduces, and in round 1 rank 0 ran them eagerly while ranks 1..7 captured a new
+    # graph around the same collectives (SCALE_r01: 8-GPU run hung, GPU 0 busy, GPUs 1-7 idle).
+    barrier()
     lib.check(L.cg_set_concurrency(0))
-    if rank == 0:
-        lib.check(L.cg_profile_enable(1))
-    # EVERY rank runs these steps: each contains the gradient all-reduces, and a rank-0-only pass deadlocked the
-    # first 2-GPU runs (rank 0 waiting in ncclAllReduce for ranks that had already finished)
+    lib.check(L.cg_profile_enable(1))
     for i in range(kp):
         dev_step(W + i, False)
     barrier()
+    buf = C.create_string_buffer(1 << 17)
+    lib.check(L.cg_profile_report(buf, len(buf)))
+    lib.check(L.cg_profile_enable(0))
     lib.check(L.cg_set_concurrency(1))
+    barrier()
     if rank == 0:
-        buf = C.create_string_buffer(1 << 16)
-        lib.check(L.cg_profile_report(buf, len(buf)))
-        lib.check(L.cg_profile_enable(0))
         prof = json.loads(buf.value.decode())
         tot = sum(k["ms"] for k in prof)
         prof.sort(key=lambda k: -k["ms"])
@@ -335,13 +392,19 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # bounded sample (~20-30 s of CPU work): 1 untimed + 2 timed steps of the SAME config (batch B) with the PyTorch-CPU restatement
+        # (BASELINE.md section 3 "B-mkl"), and one step of the C oracle port at half the batch beside it
         from oracle import pyoracle as _po
         cores = _po.usable_cpus()
-        Bs = sample_batch(cores)
-        v, dt = cpu_baseline(Bs, cores, steps=1, warm=0)
-        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "one adversarial.train loop body of the same G32up-c+D32_st3 RGB workload at batch %d (GPU arm: %d) taking %.1f s, oracle port with %d OpenMP threads; "
-                         "Torch7/LuaJIT do not exist in this image" % (Bs, B, dt, cores)}
+        Tc = _TorchCpu(cores, B=B)
+        Tc.step()
+        dt = float(np.mean([Tc.step() for _ in range(2)]))
+        ov, odt = cpu_oracle_port(B // 2, cores, steps=1)
+        cpu = {"value": B / dt, "unit": "images/s", "cores": cores, "kind": "port", "host": cpu_info(),
+               "sample": "2 timed adversarial.train loop bodies of the same G32up-c+D32_st3 RGB workload at batch %d (%.1f s each), PyTorch-CPU fp32 restatement "
+                         "(oracle/torch_step.py, oneDNN/MKL) with %d threads; Torch7/LuaJIT do not exist in this image" % (B, dt, cores),
+               "oracle_port": {"value": ov, "unit": "images/s", "cores": cores,
+                               "sample": "one step at batch %d (%.1f s) of the C restatement of the Torch7 nn CPU algorithms (oracle/catgen_oracle.c), %d OpenMP threads" % (B // 2, odt, cores)}}
 
     if rank == 0:
         fl = step_flops(B)
@@ -363,6 +426,8 @@ def main():
     stage("done")
     faulthandler.cancel_dump_traceback_later()
     L.cg_dev_free(real_d); L.cg_dev_free(zd_d); L.cg_dev_free(zg_d)
+    for ptr in (p_real, p_zd, p_zg, p_out):
+        L.cg_host_free(ptr)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -60,6 +60,9 @@ def load():
     L.cg_dev_alloc.restype = C.c_void_p
     L.cg_dev_alloc.argtypes = [C.c_int64]
     L.cg_dev_free.argtypes = [C.c_void_p]
+    L.cg_host_alloc.restype = C.c_void_p
+    L.cg_host_alloc.argtypes = [C.c_int64]
+    L.cg_host_free.argtypes = [C.c_void_p]
     L.cg_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.cg_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.cg_uniform_dev.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_uint64, C.c_uint64]

@@ -48,6 +48,7 @@ static void* grow(void** p, size_t* cap, size_t bytes) {
   cudaStreamSynchronize(ctx().stream);
   if (*p) cudaFree(*p);
   size_t want = bytes + bytes / 4 + 4096;
+  ctx().alloc_gen++;   // captured step graphs hold raw pointers into these buffers (train_step_run re-captures)
   if (cudaMalloc(p, want) != cudaSuccess) { *p = nullptr; *cap = 0; set_err(CG_ERR_CUDA, "cudaMalloc(%zu) failed", want); return nullptr; }
   *cap = want;
   return *p;
@@ -152,6 +153,7 @@ void* pinned(size_t bytes) {
 int DBuf::ensure(size_t nfloats) {
   if (n >= nfloats && p) return CG_OK;
   if (p) { cudaStreamSynchronize(ctx().stream); cudaFree(p); p = nullptr; n = 0; }
+  ctx().alloc_gen++;
   if (nfloats == 0) nfloats = 1;
   if (cudaMalloc(&p, sizeof(float) * nfloats) != cudaSuccess) { p = nullptr; return set_err(CG_ERR_CUDA, "cudaMalloc(%zu floats) failed", nfloats); }
   n = nfloats;
@@ -180,6 +182,32 @@ struct Tmp {
   ~Tmp() { cudaStreamSynchronize(ctx().stream); for (void* p : v) cudaFree(p); }
 };
 }  // namespace cg
+namespace cg {
+// sum over ranks, in place, on the current stream (graph-capturable); no-op for one rank
+int dist_allreduce_sum_f32(float* buf, long n) {
+  if (ctx().world <= 1) return CG_OK;
+#ifdef CG_WITH_NCCL
+  CG_NCCL_API();
+  ncclResult_t r = N.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", N.GetErrorString(r));
+  return CG_OK;
+#else
+  return set_err(CG_ERR_NCCL, "library built without NCCL");
+#endif
+}
+int dist_allreduce_sum_f64(double* buf, long n) {
+  if (ctx().world <= 1) return CG_OK;
+#ifdef CG_WITH_NCCL
+  CG_NCCL_API();
+  ncclResult_t r = N.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
+  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", N.GetErrorString(r));
+  return CG_OK;
+#else
+  return set_err(CG_ERR_NCCL, "library built without NCCL");
+#endif
+}
+}  // namespace cg
+
 using namespace cg;
 
 extern "C" {
@@ -418,8 +446,7 @@ int cg_dist_allreduce_grads(cg_model* m) {
 #ifdef CG_WITH_NCCL
   // sum over ranks then scale by 1/world: BCE is a mean over the LOCAL batch
   CG_NCCL_API();
-  ncclResult_t r = N.AllReduce(m->G, m->G, (size_t)m->np, ncclFloat, ncclSum, (ncclComm_t)ctx().nccl, ctx().stream);
-  if (r != ncclSuccess) return set_err(CG_ERR_NCCL, "ncclAllReduce: %s", N.GetErrorString(r));
+  CG_TRY(cg::dist_allreduce_sum_f32(m->G, m->np));
   return scale_inplace(m->G, 1.f / ctx().world, m->np);
 #else
   return set_err(CG_ERR_NCCL, "library built without NCCL");
@@ -446,7 +473,7 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     CG_TRY(G_forward_dev(G, zD + (size_t)k * hB * nz, hB, t->inputs.p + hB * img));
     // fevalG's generator forward depends on nothing fevalD changes (G's parameters move only in fevalG; its BN running
     // statistics are updated in issue order): start it now on its own lane, beside D's forward/backward/Adam below.
-    if (k == c->d_iters - 1 && c->g_iters > 0 && ctx().lanes_on) {
+    if (k == c->d_iters - 1 && c->g_iters > 0 && ctx().lanes_on && !(ctx().sync_bn && ctx().world > 1)) {   // sync-BN: G's forward holds collectives, keep ONE issue order on the communicator
       CG_TRY(lanes_fork(4, 1));
       int st;
       { LaneGuard lane(4); st = lane.status; if (st == CG_OK) st = G_forward_dev(G, zG, B, t->samples.p); }
@@ -458,10 +485,10 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     CG_TRY(D_forward_dev(D, t->inputs.p, B, t->dout.p, nullptr));
     CG_TRY(bce(t->dout.p, tgtD, B, t->scal.p + si, t->df.p));
     CG_TRY(D_backward_dev(D, t->df.p, nullptr));
-    CG_TRY(cg_dist_allreduce_grads(D));
-    CG_TRY(penalty_clamp(D->G, D->P, D->np, c->D_L1, c->D_L1, c->D_L2, c->D_clamp, t->scal.p + si + 1));
+    CG_TRY(dist_allreduce_sum_f32(D->G, D->np));   // BCE is a mean over the LOCAL batch: sum over ranks, 1/world folded into the pass below
+    CG_TRY(penalty_clamp_adam(D->G, D->P, t->mD, t->vD, D->np, 1.f / ctx().world, c->D_L1, c->D_L1, c->D_L2, c->D_clamp, t->scal.p + si + 1,
+                              t->t_dev + 0, c->lr, c->beta1, c->beta2, c->eps)); D->dirty = true;   // :92-112 then optim.adam :245
     si += 2;
-    CG_TRY(adam(D->P, D->G, t->mD, t->vD, D->np, t->t_dev + 0, c->lr, c->beta1, c->beta2, c->eps)); D->dirty = true;   // :245
   }
   for (int k = 0; k < c->g_iters; ++k) {
     // fevalG_on_D (adversarial.lua:171-215)
@@ -479,10 +506,10 @@ static int train_step_core(cg_trainer* t, const cg_step_cfg* c, const float* rea
     D->skip_param_grads = 0;
     CG_TRY(bst);
     CG_TRY(G_backward_dev(G, t->gimg.p, nullptr));
-    CG_TRY(cg_dist_allreduce_grads(G));
-    CG_TRY(penalty_clamp(G->G, G->P, G->np, c->G_L1, c->G_L2, c->G_L2, c->G_clamp, t->scal.p + si + 1));   // sign term uses G_L2 (adversarial.lua:206)
+    CG_TRY(dist_allreduce_sum_f32(G->G, G->np));
+    CG_TRY(penalty_clamp_adam(G->G, G->P, t->mG, t->vG, G->np, 1.f / ctx().world, c->G_L1, c->G_L2, c->G_L2, c->G_clamp, t->scal.p + si + 1,   // sign term uses G_L2 (adversarial.lua:206)
+                              t->t_dev + 1, c->lr, c->beta1, c->beta2, c->eps)); G->dirty = true;   // :201-212 then optim.adam :262
     si += 2;
-    CG_TRY(adam(G->P, G->G, t->mG, t->vG, G->np, t->t_dev + 1, c->lr, c->beta1, c->beta2, c->eps)); G->dirty = true;   // :262
   }
   return CG_OK;
 }
@@ -509,8 +536,14 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   bool eligible = X.graph_mode && !X.prof_on && !(t->D->mq && t->D->mq_next < t->D->mq_count);
   if (!eligible) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   cg_trainer::StepGraph* sg = nullptr;
-  for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg)) && e.engine == X.conv_engine && e.elim == X.dead_grad_elim && e.lanes == X.lanes_on * 2 + X.side_on) { sg = &e; break; }
-  if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; sg->engine = X.conv_engine; sg->elim = X.dead_grad_elim; sg->lanes = X.lanes_on * 2 + X.side_on; }
+  // the key holds everything the recorded launch sequence depends on besides buffer addresses (those: alloc_gen below)
+  const int mode_key = X.lanes_on * 2 + X.side_on + 4 * t->G->training + 8 * t->D->training + 16 * X.sync_bn + 32 * X.world;
+  for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg)) && e.engine == X.conv_engine && e.elim == X.dead_grad_elim && e.lanes == mode_key) { sg = &e; break; }
+  if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; sg->engine = X.conv_engine; sg->elim = X.dead_grad_elim; sg->lanes = mode_key; }
+  // A graph bakes in raw device pointers (DBufs, workspaces, lane / side scratch).  Any reallocation since the capture --
+  // a larger configuration, a larger eager forward -- makes them dangle: drop the graph, run one eager step so that every
+  // buffer reaches its size again, and capture anew.
+  if (sg->exec && sg->gen != X.alloc_gen) { cudaGraphExecDestroy(sg->exec); sg->exec = nullptr; sg->warm = 1; }
   const int B = c->B, hB = B / 2; const size_t img = (size_t)t->G->C * 1024, nz = t->G->nz;
   const size_t nr = (size_t)c->d_iters * hB * img, nzd = (size_t)c->d_iters * hB * nz, nzg = (size_t)c->g_iters * B * nz;
   if (sg->failed || (!sg->exec && sg->warm < 2)) {
@@ -525,17 +558,29 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   if (!sg->exec) {
     int64_t l0 = X.launches;
     cudaGraph_t graph = nullptr;
+    // the graph must contain both repacks at their first use, whatever eager forwards ran since the last update
+    t->G->dirty = t->D->dirty = true;
+    const uint64_t gen0 = X.alloc_gen;
     if (cudaStreamBeginCapture(X.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); sg->failed = true; }
     else {
       int st = train_step_core(t, c, g0, g0 + nr, g0 + nr + nzd, nullptr, nullptr);
       cudaError_t e = cudaStreamEndCapture(X.stream, &graph);
       if (st != CG_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&sg->exec, graph, 0) != cudaSuccess) { cudaGetLastError(); sg->exec = nullptr; sg->failed = true; }
       if (graph) cudaGraphDestroy(graph);
+      if (!sg->failed && X.alloc_gen != gen0) {             // a buffer grew during capture (illegal in capture anyway): never replay this
+        cudaGraphExecDestroy(sg->exec); sg->exec = nullptr; sg->warm = 1;
+        X.launches = l0;
+        CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG);
+      }
+      sg->gen = X.alloc_gen;
       sg->launches = X.launches - l0; X.launches = l0;      // captured, not executed yet
     }
     if (sg->failed) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   }
   CG_CUDA(cudaGraphLaunch(sg->exec, X.stream));
+  // the replay ran both Adam updates on the device: the packed operands are stale for any eager forward that follows
+  // (the replayed graph itself repacks at first use, see above)
+  t->G->dirty = t->D->dirty = true;
   X.launches += sg->launches;
   return read_losses(t, c, lossD, lossG);
 }
@@ -562,6 +607,8 @@ int cg_train_step(cg_trainer* t, const cg_step_cfg* cfg, const float* real, cons
 }
 void* cg_dev_alloc(int64_t bytes) { if (!ctx().inited) return nullptr; void* p = nullptr; if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr; return p; }
 int cg_dev_free(void* p) { if (p) { cudaStreamSynchronize(ctx().stream); cudaFree(p); } return CG_OK; }
+void* cg_host_alloc(int64_t bytes) { if (!ctx().inited) return nullptr; void* p = nullptr; if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+int cg_host_free(void* p) { if (p) { cudaStreamSynchronize(ctx().stream); cudaFreeHost(p); } return CG_OK; }
 int cg_dev_upload(void* dst, const void* src, int64_t bytes) { CG_REQUIRE_INIT(); CG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
 int cg_dev_download(void* dst, const void* src, int64_t bytes) { CG_REQUIRE_INIT(); CG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK; }
 int cg_uniform_dev(float* dst, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset) { CG_REQUIRE_INIT(); return uniform(dst, n, lo, hi, seed, offset); }
@@ -592,6 +639,8 @@ int cg_dist_init(int rank, int world, const char id[128]) {
 #endif
 }
 int cg_dist_world(void) { return ctx().world; }
+int cg_dist_set_sync_bn(int on) { ctx().sync_bn = on ? 1 : 0; return CG_OK; }
+int cg_dist_get_sync_bn(void) { return ctx().sync_bn; }
 
 // ------------------------------------------------------------------ op level (Torch NCHW host tensors)
 static int conv_op_args(int N, int Ci, int H, int W, int Co, int k) {

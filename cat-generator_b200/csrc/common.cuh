@@ -21,6 +21,7 @@ struct Ctx {
   int dead_grad_elim = 1;       // cg_train_step: skip D's parameter gradients inside fevalG (zeroed unread by the next fevalD)
   int graph_mode = 1;           // replay the training step as a CUDA graph once warm (cg_set_graph_mode)
   int64_t launches = 0;
+  uint64_t alloc_gen = 0;       // bumped whenever a device buffer a captured step graph may point into is (re)allocated
   char err[1024] = {0};
   // scratch (grown on demand, stream-ordered reuse)
   void* ws = nullptr; size_t ws_bytes = 0;
@@ -46,6 +47,7 @@ struct Ctx {
   // data parallel
   int rank = 0, world = 1;
   void* nccl = nullptr;
+  int sync_bn = 0;              // data parallel: batch-norm statistics over the GLOBAL batch (all-reduced sums) instead of per rank
   // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
   bool prof_on = false;
   double next_flops = 0, next_bytes = 0;

@@ -384,7 +384,7 @@ static int stn_backward(cg_model* m, cg_stn* s, const float* gout, float* gin, i
 
 static int ensure_masks(cg_model* d, int B) {
   long n = D_mask_floats(B);
-  if (d->masks_n < n) { if (d->masks) { cudaStreamSynchronize(ctx().stream); cudaFree(d->masks); } CG_CUDA(cudaMalloc(&d->masks, sizeof(float) * n)); d->masks_n = n; }
+  if (d->masks_n < n) { if (d->masks) { cudaStreamSynchronize(ctx().stream); cudaFree(d->masks); } ctx().alloc_gen++; CG_CUDA(cudaMalloc(&d->masks, sizeof(float) * n)); d->masks_n = n; }
   d->masks_B = B;
   if (d->mq && d->mq_next < d->mq_count) {   // masks queued by cg_D_set_masks: one set per forward, in order
     if (d->mq_B != B) return set_err(CG_ERR_ARG, "queued dropout masks are for batch %d, forward has batch %d", d->mq_B, B);

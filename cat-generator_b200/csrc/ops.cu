@@ -262,6 +262,14 @@ __device__ __forceinline__ void col_partials(const double* __restrict__ part, in
   for (int s = lane; s < S; s += 32) { s0 += part[((long)s * C + c) * 2]; s1 += part[((long)s * C + c) * 2 + 1]; }
   s0 = warp_sum_d(s0); s1 = warp_sum_d(s1);
 }
+// per-column totals of the split partials (fixed order): the quantity sync-BN all-reduces
+__global__ void k_col_totals(const double* __restrict__ part, int S, int C, double* __restrict__ tot) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s0, s1; col_partials(part, S, C, c, lane, s0, s1);
+  if (lane) return;
+  tot[2 * c] = s0; tot[2 * c + 1] = s1;
+}
 // nn.SpatialBatchNormalization training forward (A.3): biased batch variance for normalisation,
 // unbiased into running_var, momentum 0.1
 __global__ void k_bn_stats_final(const double* __restrict__ part, int S, int C, double m, float eps, float mom,
@@ -286,11 +294,19 @@ int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y
                  float* run_mean, float* run_var, long M, int C, float eps, float mom) {
   int S = colreduce_splits(M, C);
   long rps = (M + S - 1) / S;
-  double* part = (double*)workspace(sizeof(double) * 2 * (size_t)S * C);
+  double* part = (double*)workspace(sizeof(double) * 2 * (size_t)(S + 1) * C);
   if (!part) return CG_ERR_CUDA;
   dim3 g(cdiv(C, 32), S), b(32, 8);
+  ctx().next_bytes = 4.0 * (double)M * C;
   CG_LAUNCH(k_colreduce<0>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
-  CG_LAUNCH(k_bn_stats_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, eps, mom, mean, invstd, run_mean, run_var);
+  if (ctx().sync_bn && ctx().world > 1) {
+    // sync-BN: statistics over the GLOBAL batch = all-reduced per-channel (sum, sum of squares), 2*C doubles
+    double* tot = part + 2 * (size_t)S * C;
+    CG_LAUNCH(k_col_totals, cdiv(C, 4), 128, 0, part, S, C, tot);
+    CG_TRY(dist_allreduce_sum_f64(tot, 2L * C));
+    CG_LAUNCH(k_bn_stats_final, cdiv(C, 4), 128, 0, tot, 1, C, (double)M * ctx().world, eps, mom, mean, invstd, run_mean, run_var);
+  } else
+    CG_LAUNCH(k_bn_stats_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, eps, mom, mean, invstd, run_mean, run_var);
   long n = M * C;
   if (y) CG_LAUNCH(k_bn_apply, grid1d(n, 256, 4), 256, 0, x, gamma, beta, mean, invstd, y, n, C);   // y == nullptr: statistics only (the caller fuses the apply)
   return CG_OK;
@@ -325,17 +341,36 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ x, const float* __restr
     gx[i] = gamma[c] * invstd[c] * (gy[i] - mg[c] - xh * mgx[c]);
   }
 }
+// sync-BN backward: the means in gx are over the GLOBAL batch, while ggamma / gbeta accumulate this rank's LOCAL sums -- the
+// parameter-gradient all-reduce (sum over ranks, scaled 1/world with the rest of the flat vector) then yields the gradient of the
+// global-mean loss, exactly what one device with the whole batch computes.
+__global__ void k_bn_bwd_final_sync(const double* __restrict__ tot_local, const double* __restrict__ tot_glob, int C, double m_glob,
+                                    float* __restrict__ mg, float* __restrict__ mgx, float* __restrict__ ggamma_acc, float* __restrict__ gbeta_acc) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mg[c] = (float)(tot_glob[2 * c] / m_glob); mgx[c] = (float)(tot_glob[2 * c + 1] / m_glob);
+  if (gbeta_acc) gbeta_acc[c] += (float)tot_local[2 * c];
+  if (ggamma_acc) ggamma_acc[c] += (float)tot_local[2 * c + 1];
+}
 int bn_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* invstd,
            float* gx, float* ggamma_acc, float* gbeta_acc, long M, int C) {
   int S = colreduce_splits(M, C);
   long rps = (M + S - 1) / S;
-  size_t pbytes = sizeof(double) * 2 * (size_t)S * C;
+  size_t pbytes = sizeof(double) * 2 * (size_t)(S + 2) * C;
   char* wsb = (char*)workspace(pbytes + sizeof(float) * 2 * C);
   if (!wsb) return CG_ERR_CUDA;
   double* part = (double*)wsb; float* mg = (float*)(wsb + pbytes); float* mgx = mg + C;
   dim3 g(cdiv(C, 32), S), b(32, 8);
+  ctx().next_bytes = 8.0 * (double)M * C;
   CG_LAUNCH(k_colreduce<1>, g, b, 0, x, gy, mean, invstd, part, M, C, rps);
-  CG_LAUNCH(k_bn_bwd_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, mg, mgx, ggamma_acc, gbeta_acc);
+  if (ctx().sync_bn && ctx().world > 1) {
+    double* tot = part + 2 * (size_t)S * C; double* totg = tot + 2 * (size_t)C;
+    CG_LAUNCH(k_col_totals, cdiv(C, 4), 128, 0, part, S, C, tot);
+    CG_CUDA(cudaMemcpyAsync(totg, tot, sizeof(double) * 2 * C, cudaMemcpyDeviceToDevice, ctx().stream));
+    CG_TRY(dist_allreduce_sum_f64(totg, 2L * C));
+    CG_LAUNCH(k_bn_bwd_final_sync, cdiv(C, 128), 128, 0, tot, totg, C, (double)M * ctx().world, mg, mgx, ggamma_acc, gbeta_acc);
+  } else
+    CG_LAUNCH(k_bn_bwd_final, cdiv(C, 4), 128, 0, part, S, C, (double)M, mg, mgx, ggamma_acc, gbeta_acc);
   if (gx) { long n = M * C; CG_LAUNCH(k_bn_bwd_apply, grid1d(n, 256, 4), 256, 0, x, gy, gamma, mean, invstd, mg, mgx, gx, n, C); }
   return CG_OK;
 }
@@ -642,6 +677,53 @@ __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float
 int adam(float* x, const float* g, float* m, float* v, long n, int* t_dev, float lr, float b1, float b2, float eps) {
   CG_LAUNCH(k_inc_i32, 1, 1, 0, t_dev);
   CG_LAUNCH(k_adam, grid1d(n, 256, 4), 256, 0, x, g, m, v, n, (const int*)t_dev, lr, b1, b2, eps); return CG_OK;
+}
+// penalty + clamp + Adam fused (see ops.cuh).  The norms are taken from p BEFORE the update, as adversarial.lua:92-98 does.
+__global__ void k_penalty_clamp_adam(float* __restrict__ g, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, long n, float gscale,
+                                     float l1sign, float l2, float clampv, int want_norms, double* __restrict__ part,
+                                     const int* __restrict__ t_dev, float lr, float b1, float b2, float eps) {
+  __shared__ float step_s;
+  if (threadIdx.x == 0) {
+    int t = *t_dev;
+    step_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  }
+  __syncthreads();
+  const float step = step_s;
+  const bool pen = (l1sign != 0.f) || (l2 != 0.f);
+  double n1 = 0, n2 = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float pv = x[i], gv = g[i];
+    if (gscale != 1.f) gv *= gscale;
+    if (want_norms) { n1 += fabs((double)pv); n2 += (double)pv * pv; }
+    if (pen) gv += (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)) * l1sign + pv * l2;
+    if (clampv != 0.f) gv = fminf(fmaxf(gv, -clampv), clampv);
+    g[i] = gv;
+    float mv = b1 * m[i] + (1.f - b1) * gv;
+    float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    m[i] = mv; v[i] = vv;
+    x[i] = pv - step * mv / (sqrtf(vv) + eps);
+  }
+  if (want_norms) {
+    n1 = block_sum_d(n1); n2 = block_sum_d(n2);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2] = n1; part[blockIdx.x * 2 + 1] = n2; }
+  }
+}
+int penalty_clamp_adam(float* g, float* p, float* m, float* v, long n, float gscale, float l1, float l1sign, float l2, float clampv, float* loss_add_dev,
+                       int* t_dev, float lr, float b1, float b2, float eps) {
+  bool pen = (l1 != 0.f) || (l2 != 0.f);
+  if (!pen) { l1sign = 0.f; l2 = 0.f; }
+  int gsz = grid1d(n, 256, 4);
+  int want = (loss_add_dev && pen) ? 1 : 0;
+  double* part = (double*)workspace(sizeof(double) * 2 * gsz);
+  if (!part) return CG_ERR_CUDA;
+  CG_LAUNCH(k_inc_i32, 1, 1, 0, t_dev);
+  ctx().next_bytes = 32.0 * (double)n;   // read g, p, m, v ; write g, p, m, v
+  CG_LAUNCH(k_penalty_clamp_adam, gsz, 256, 0, g, p, m, v, n, gscale, l1sign, l2, clampv, want, part, (const int*)t_dev, lr, b1, b2, eps);
+  if (loss_add_dev) {
+    if (want) CG_LAUNCH(k_penalty_final, 1, 256, 0, part, gsz, l1, l2, loss_add_dev);
+    else CG_CUDA(cudaMemsetAsync(loss_add_dev, 0, sizeof(float), ctx().stream));
+  }
+  return CG_OK;
 }
 __global__ void k_uniform(float* __restrict__ dst, long n, float lo, float hi, uint32_t k0, uint32_t k1, uint64_t offset) {
   long nq = (n + 3) / 4;

@@ -53,6 +53,14 @@ int bce(const float* p, const float* t, int n, float* loss_dev, float* g);
 // g += sign(p)*l1sign + p*l2; clamp; *loss_add_dev = l1*|p|_1 + l2*|p|^2/2 (if non-null)
 int penalty_clamp(float* g, const float* p, long n, float l1, float l1sign, float l2, float clampv, float* loss_add_dev);
 int adam(float* x, const float* g, float* m, float* v, long n, int* t_dev, float lr, float b1, float b2, float eps);   // increments *t_dev, then steps
+// The optimiser tail of one closure in ONE pass over the flat vectors: g <- clamp(g*gscale + sign(p)*l1sign + p*l2) ; *loss_add_dev as
+// penalty_clamp ; then the optim.adam update with that g (t_dev incremented first).  Arithmetic per element is penalty_clamp's followed
+// by adam's, so results are bit-identical to the two-pass form.  gscale: 1/world after a data-parallel sum-all-reduce, else 1.
+int penalty_clamp_adam(float* g, float* p, float* m, float* v, long n, float gscale, float l1, float l1sign, float l2, float clampv, float* loss_add_dev,
+                       int* t_dev, float lr, float b1, float b2, float eps);
+// data parallel (capi.cu): in-place sum over ranks on the current stream; no-ops for one rank
+int dist_allreduce_sum_f32(float* buf, long n);
+int dist_allreduce_sum_f64(double* buf, long n);
 int uniform(float* dst, long n, float lo, float hi, uint64_t seed, uint64_t offset);
 // dst[i] = (u >= p_drop) ? keep_value : 0
 int bernoulli_mask(float* dst, long n, float p_drop, float keep_value, uint64_t seed, const unsigned long long* offset_dev, uint64_t rel);

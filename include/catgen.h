@@ -146,6 +146,10 @@ void* cg_dev_alloc(int64_t bytes);            /* helpers for callers that keep i
 int   cg_dev_free(void* p);
 int   cg_dev_upload(void* dst_dev, const void* src_host, int64_t bytes);
 int   cg_dev_download(void* dst_host, const void* src_dev, int64_t bytes);
+/* page-locked host memory (cudaMallocHost): what a caller stages its batches in so that the H2D copies of cg_train_step run at
+   link speed and asynchronously (bench.py's end-to-end region) */
+void* cg_host_alloc(int64_t bytes);
+int   cg_host_free(void* p);
 /* U(lo,hi) noise on the device: NN_UTILS.createNoiseInputs (utils/nn_utils.lua:35-39) */
 int   cg_uniform_dev(float* dst_dev, int64_t n, float lo, float hi, uint64_t seed, uint64_t offset);
 
@@ -156,6 +160,12 @@ int cg_dist_unique_id(char id_out[128]);
 int cg_dist_init(int rank, int world, const char id[128]);
 int cg_dist_allreduce_grads(cg_model* m);
 int cg_dist_world(void);
+/* Batch norm under data parallelism (SURVEY.md section 8e "BN caveat").  0 (default): G's three SpatialBatchNormalization layers use
+   the statistics of each rank's LOCAL batch -- no extra collective, but not what one device with the whole batch computes.
+   1: sync-BN -- per-channel (sum, sum of squares) and the two backward sums are all-reduced (2*C doubles each), so an R-rank step
+   equals the single-device step on the concatenated batch. */
+int cg_dist_set_sync_bn(int on);
+int cg_dist_get_sync_bn(void);
 
 /* ------------------------------------------------------------------ op level (one call per nn.Module method) */
 /* nn.SpatialConvolution / cudnn.SpatialConvolution updateOutput, updateGradInput, accGradParameters */

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz -- float64 reference values for small seeded cases of the hot path.
 
 Where the numbers come from: the reference (Lua/Torch7) cannot run in this environment and ships no golden vectors, so these
-are produced by the float64 PyTorch-autograd restatement of the reference's networks in tests/torch_ref.py (models.lua:138-160,
+are produced by the float64 PyTorch-autograd restatement of the reference's networks in oracle/torch_ref.py (models.lua:138-160,
 196-228, 640-711, 814-906), which shares no code with the C oracle or the CUDA kernels.  They pin BOTH: tests/test_golden.py
 checks the oracle against them on CPU and the CUDA path against them on the GPU box, where neither this script nor torch_ref runs.
 
@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 from oracle import pyoracle as po
-import torch_ref as tr
+from oracle import torch_ref as tr
 
 torch.set_num_threads(8)
 NSAMP = 4096

@@ -1,0 +1,340 @@
+"""GPU parity at the BASELINE.json configurations and the robustness cases round 1 left untested.
+
+  * c2 = G32up-c + D32_st3, RGB, batch 128 (models.lua:196-228); c3 = G32up, RGB, batch 256, --D_iterations=2
+    (models.lua:138-160, adversarial.lua:221-249): both closures against the oracle at FULL batch size, and the fused
+    cg_train_step with d_iters = 2 against og_train_step.
+  * CUDA-graph replay: eager forwards interleaved with replayed steps (the host-side `dirty` flag), and buffers that regrow
+    after a capture (stale pointers inside an instantiated graph).
+  * the GPU initialiser's distribution (weight-init.lua:40-75, models.lua:857-860), the epoch loop of adversarial.train
+    (adversarial.lua:51-68,101-106,286-291) and a checkpoint round trip on the real models (train.lua:252-261,127-137).
+Measured errors are printed (pytest -s / the log the builder commits under profiles/); the asserted bounds are stated where
+they are used.  The oracle is the checker only.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyoracle as po                 # noqa: E402
+from catgen import lib, models, adversarial, checkpoint  # noqa: E402
+from test_gpu_parity import _closure_inputs, _gpu_fevalD, _gpu_fevalG, rel, l2rel   # noqa: E402
+
+P = lib.P
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    lib.init(0)
+    po.lib().og_set_threads(po.usable_cpus())
+    yield
+    po.lib().og_set_threads(min(po.usable_cpus(), 16))
+
+
+def _report(name, **kv):
+    print("[parity %s] " % name + "  ".join("%s=%.3e" % (k, v) for k, v in kv.items()))
+
+
+# ------------------------------------------------------------------ closures at BASELINE size
+@pytest.mark.parametrize("gk,ok,Cc,B", [(lib.G32UPC, po.G32UPC, 3, 128), (lib.G32UP, po.G32UP, 3, 256)], ids=["c2-G32upc-B128", "c3-G32up-B256"])
+def test_closures_match_oracle_at_baseline_size(gk, ok, Cc, B):
+    """fevalD and fevalG_on_D (adversarial.lua:72-215) on the SHIPPED engine with the configuration's real batch size.
+    Bounds: generated pixels <= 1e-3 max-abs (north_star); D's sigmoid outputs <= 1e-3; closure losses <= 2e-3;
+    gradients relative to max|oracle| as gtol below (the fp16 forward of G moves PReLU decisions; see test_gpu_parity's
+    module docstring, statement (c))."""
+    L = lib.load()
+    rng = np.random.default_rng(50 + B)
+    og, od = po.Model(ok, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
+    g = models.create_G((Cc, 32, 32), 100, kind=gk); d = models.create_D((Cc, 32, 32), True)
+    g.set_params(og.params); g.set_bn_running(og.bn_running); d.set_params(od.params)
+    ot = po.Trainer(og, od)
+    cfg, ocfg = lib.default_cfg(B), po.default_cfg(B)
+    real, zD, zG, maskD, maskG = _closure_inputs(rng, Cc, B)
+    inputs, targets, out, f, gD = _gpu_fevalD(L, g, d, cfg, real, zD, maskD, B)
+    fake0 = og.G_forward(zD, True)
+    e_px = float(np.abs(inputs[B // 2:] - fake0).max())
+    dout0 = np.zeros(B, np.float32)
+    f0 = po.lib().og_fevalD(ot.h, C.byref(ocfg), po.P(np.concatenate([real, fake0]).astype(np.float32)), po.P(targets), po.P(maskD), po.P(dout0))
+    e_out, e_gD = float(np.abs(out - dout0).max()), rel(gD, od.grads)
+    _report("fevalD B=%d" % B, pixels=e_px, d_out=e_out, loss=abs(f - f0), gradD_rel_max=e_gD, gradD_l2=l2rel(gD, od.grads))
+    assert e_px < 1e-3 and e_out < 1e-3 and abs(f - f0) < 2e-3
+    assert e_gD < 2e-2
+    # fevalG_on_D with D's parameters as they are (no update in between: gradients, not trajectories, carry the claim)
+    g.set_bn_running(og.bn_running)
+    outG, fG, gimg, gG = _gpu_fevalG(L, g, d, cfg, zG, maskG, B)
+    fG0 = po.lib().og_fevalG_on_D(ot.h, C.byref(ocfg), po.P(zG), po.P(maskG))
+    e_gG = rel(gG, og.grads)
+    _report("fevalG B=%d" % B, loss=abs(fG - fG0), gradG_rel_max=e_gG, gradG_l2=l2rel(gG, og.grads))
+    assert abs(fG - fG0) < 2e-3
+    assert e_gG < 5e-2
+
+
+def test_c3_fused_step_with_two_D_iterations_tracks_oracle():
+    """BASELINE configs[2]: G32up RGB, batch 256, --D_iterations=2 through ONE cg_train_step call against og_train_step
+    (adversarial.lua:221-249 repeats the whole D block -- new reals, new fakes, another Adam step).  lossD[0] and d-phase outputs of
+    the first iteration are exact-input parity; everything behind the first Adam update is compared at the trajectory floor the
+    oracle has against itself (profiles/r01_parity_noise_floor.txt: 8e-4 on the loss)."""
+    rng = np.random.default_rng(77)
+    Cc, B, d_it = 3, 256, 2
+    og, od = po.Model(po.G32UP, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
+    g = models.create_G((Cc, 32, 32), 100, kind=lib.G32UP); d = models.create_D((Cc, 32, 32), True)
+    g.set_params(og.params); g.set_bn_running(og.bn_running); d.set_params(od.params)
+    t, ot = adversarial.Trainer(g, d), po.Trainer(og, od)
+    real = rng.uniform(0, 1, (d_it, B // 2, Cc, 32, 32)).astype(np.float32)
+    zD = rng.uniform(-1, 1, (d_it, B // 2, 100)).astype(np.float32)
+    zG = rng.uniform(-1, 1, (1, B, 100)).astype(np.float32)
+    masks = np.stack([po.make_D_masks(B, rng) for _ in range(d_it + 1)])
+    d.set_masks(masks, B, d_it + 1)
+    lD, lG, dout = t.step(lib.default_cfg(B, d_it, 1), real, zD, zG)
+    lD0, lG0, dout0 = ot.step(po.default_cfg(B, d_it, 1), real, zD, zG, masks)
+    _report("c3 step", lossD0=abs(lD[0] - lD0[0]), lossD1=abs(lD[1] - lD0[1]), lossG=abs(lG[0] - lG0[0]), d_out=float(np.abs(dout - dout0).max()))
+    assert abs(lD[0] - lD0[0]) < 2e-3
+    assert abs(lD[1] - lD0[1]) < 5e-3 and abs(lG[0] - lG0[0]) < 5e-3
+    assert np.abs(dout - dout0).max() < 1e-2
+    # both D updates and the G update happened: Adam's sign-like first steps move (almost) every parameter
+    assert np.mean(d.get_params() != od.params) > 0 and np.mean(np.abs(d.get_params() - od.params) > 1.5e-3) < 2e-2
+
+
+def test_two_D_iterations_fused_equals_per_module_sequence():
+    """d_iters = 2 inside cg_train_step is exactly 2 x (fevalD + adam) then fevalG + adam through the per-module calls (GPU against GPU)."""
+    L = lib.load()
+    rng = np.random.default_rng(8)
+    Cc, B = 3, 8
+    og, od = po.Model(po.G32UP, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
+    seedp, seedd = og.params.copy(), od.params.copy()
+    ins = [_closure_inputs(rng, Cc, B) for _ in range(2)]
+    real = np.stack([i[0] for i in ins]); zD = np.stack([i[1] for i in ins]); zG = ins[0][2][None]
+    mD = [i[3] for i in ins]; mG = ins[0][4]
+    cfg = lib.default_cfg(B, 2, 1)
+    ga = models.create_G((Cc, 32, 32), 100, kind=lib.G32UP); da = models.create_D((Cc, 32, 32), True); ga.set_params(seedp); da.set_params(seedd)
+    ta = adversarial.Trainer(ga, da)
+    da.set_masks(np.stack(mD + [mG]), B, 3)
+    lD, lG, dout = ta.step(cfg, real, zD, zG)
+    gb = models.create_G((Cc, 32, 32), 100, kind=lib.G32UP); db = models.create_D((Cc, 32, 32), True); gb.set_params(seedp); db.set_params(seedd)
+    tb = adversarial.Trainer(gb, db)
+    fDs = []
+    for k in range(2):
+        _, _, outb, fD, _ = _gpu_fevalD(L, gb, db, cfg, real[k], zD[k], mD[k], B)
+        lib.check(L.cg_adam_step(tb.h, 0, C.byref(cfg)))
+        fDs.append(fD)
+    _, fG, _, _ = _gpu_fevalG(L, gb, db, cfg, zG[0], mG, B)
+    lib.check(L.cg_adam_step(tb.h, 1, C.byref(cfg)))
+    assert abs(lD[0] - fDs[0]) < 1e-5 and abs(lD[1] - fDs[1]) < 5e-4 and abs(lG[0] - fG) < 5e-4
+    assert np.abs(dout - outb).max() < 1e-3
+    assert np.mean(np.abs(da.get_params() - db.get_params()) > 0.5e-3) < 1e-3
+    assert np.mean(np.abs(ga.get_params() - gb.get_params()) > 0.5e-3) < 1e-3
+
+
+# ------------------------------------------------------------------ CUDA-graph robustness
+def _run_schedule(L, graph_mode, schedule, Cc=3):
+    """schedule: list of ('step', B) / ('sample', n).  Returns the recorded losses / sampled images."""
+    lib.check(L.cg_set_graph_mode(graph_mode))
+    rng = np.random.default_rng(123)
+    g = models.create_G((Cc, 32, 32), 100, seed=1); d = models.create_D((Cc, 32, 32), True, seed=2)
+    t = adversarial.Trainer(g, d)
+    rec = []
+    for what, n in schedule:
+        if what == "step":
+            real, zD, zG, _, _ = _closure_inputs(rng, Cc, n)
+            lD, lG, dout = t.step(lib.default_cfg(n), real[None], zD[None], zG[None])
+            rec.append(("step", float(lD[0]), float(lG[0])))
+        else:
+            z = rng.uniform(-1, 1, (n, 100)).astype(np.float32)
+            rec.append(("sample", g.forward(z).copy()))
+    return rec, g.get_params(), d.get_params()
+
+
+def _compare_schedules(a, b):
+    for x, y in zip(a[0], b[0]):
+        assert x[0] == y[0]
+        if x[0] == "step":
+            assert abs(x[1] - y[1]) < 5e-3 and abs(x[2] - y[2]) < 5e-3, (x, y)
+        else:
+            # a forward with packed weights one Adam update stale differs by ~lr in every weight: pixels move by >> 1e-3
+            assert np.abs(x[1] - y[1]).max() < 2e-3, "eager forward after replayed steps used stale packed weights"
+    assert np.mean(np.abs(a[1] - b[1]) > 0.5e-3) < 3e-2 and np.mean(np.abs(a[2] - b[2]) > 0.5e-3) < 3e-2
+
+
+def test_graph_replay_with_interleaved_eager_forwards():
+    """2 steps, eager G.forward, 4 more steps (capture happens right after an eager forward cleared `dirty`), eager G.forward --
+    against the same schedule with graphs off.  Without the fix the captured graph holds no repack node and G trains on frozen
+    packed weights; the sampled images then differ grossly."""
+    L = lib.load()
+    sched = [("step", 8)] * 2 + [("sample", 8)] + [("step", 8)] * 4 + [("sample", 8)] + [("step", 8)] * 2 + [("sample", 8)]
+    try:
+        ref = _run_schedule(L, 0, sched)
+        got = _run_schedule(L, 1, sched)
+    finally:
+        lib.check(L.cg_set_graph_mode(1))
+    _compare_schedules(got, ref)
+
+
+def test_graph_survives_buffer_growth():
+    """A graph captured at batch 8 holds raw pointers; batch 32 steps and a batch 64 forward then regrow the buffers.  Going back to
+    batch 8 must re-capture (allocation generation) instead of replaying into freed memory."""
+    L = lib.load()
+    sched = [("step", 8)] * 4 + [("step", 32)] * 3 + [("sample", 64)] + [("step", 8)] * 3 + [("sample", 8)]
+    try:
+        ref = _run_schedule(L, 0, sched)
+        got = _run_schedule(L, 1, sched)
+    finally:
+        lib.check(L.cg_set_graph_mode(1))
+    _compare_schedules(got, ref)
+
+
+# ------------------------------------------------------------------ A10: the GPU initialiser
+def _layout_D(C):
+    """(offset, count, kind, fan_in) runs of D32_st3's flat vector in getParameters() order (models.lua:640-711, :843-860)."""
+    runs, o = [], 0
+
+    def conv(ci, co, k, zero_bias, tag):
+        nonlocal o
+        n = co * ci * k * k
+        runs.append((o, n, "W", ci * k * k, tag)); o += n
+        runs.append((o, co, "b0" if zero_bias else "b", ci * k * k, tag)); o += co
+
+    def stn(ch, S, nth, tag):
+        nonlocal o
+        conv(ch, 16, 3, True, tag + ".c1"); conv(16, 16, 3, True, tag + ".c2")
+        f = 16 * (S // 4) ** 2
+        conv(f, 64, 1, True, tag + ".l1")
+        runs.append((o, nth * 64, "zero", 64, tag + ".l2W")); o += nth * 64
+        runs.append((o, nth, "theta", 64, tag + ".l2b")); o += nth
+
+    def prelu():
+        nonlocal o
+        runs.append((o, 1, "prelu", 1, "prelu")); o += 1
+
+    stn(C, 32, 1, "stn0")
+    conv(C, 64, 3, True, "t1"); prelu(); conv(64, 64, 3, True, "t2"); prelu()
+    for b in range(3):
+        stn(64, 16, 4, "stn%d" % (b + 1))
+        conv(64, 64, 3, False, "b%d.1" % b); prelu(); conv(64, 64, 3, False, "b%d.2" % b); prelu()
+    conv(64, 128, 5, False, "b3.1"); prelu(); conv(128, 128, 7, False, "b3.2"); prelu()
+    conv(20480, 256, 1, True, "h1"); prelu(); conv(256, 1, 1, True, "h2")
+    return runs, o
+
+
+def test_gpu_initialiser_follows_weight_init_heuristic():
+    """weight-init.lua:40-75 'heuristic' + nn defaults: W ~ U(+-1/sqrt(fan_in)); bias of every TOP-LEVEL module
+    zero; convs nested in nn.Concat keep a random bias; PReLU slope 0.25; BN gamma ~ U(0,1), beta 0; the STN's last Linear is W = 0,
+    b = identity parameters (models.lua:857-860): every transformer starts as the identity map."""
+    d = models.create_D((3, 32, 32), True, seed=123)
+    p = d.get_params()
+    runs, total = _layout_D(3)
+    assert total == d.nparams == 6664777
+    for o, n, kind, fan, tag in runs:
+        v = p[o:o + n]
+        bound = 1.0 / np.sqrt(fan)
+        if kind == "W":
+            assert np.abs(v).max() <= bound * (1 + 1e-6), tag
+            if n >= 2000:
+                assert abs(v.mean()) < 4 * bound / np.sqrt(3 * n) + 1e-7, tag       # mean of U(+-b): sd b/sqrt(3n)
+                assert abs(v.std() - bound / np.sqrt(3)) < 0.05 * bound, tag
+                assert np.abs(v).max() > 0.95 * bound, tag
+        elif kind == "b0":
+            assert np.all(v == 0), tag
+        elif kind == "b":
+            assert np.abs(v).max() <= bound * (1 + 1e-6) and np.abs(v).max() > 0, tag
+        elif kind == "zero":
+            assert np.all(v == 0), tag
+        elif kind == "theta":
+            assert v.tolist() == ([0.0] if n == 1 else [0.0, 1.0, 0.0, 0.0]), tag
+        elif kind == "prelu":
+            assert v[0] == np.float32(0.25)
+    # identity transformers: D(x) must not change when the loc-net inputs change (W = 0) -- checked functionally through STN_0:
+    # with theta = identity, the sampled image equals the input, so D's output is a function of x only through the trunk.
+    g = models.create_G((3, 32, 32), 100, seed=5)
+    q = g.get_params()
+    o = 0
+    assert np.abs(q[:8192 * 100]).max() <= 0.1 * (1 + 1e-6); o = 8192 * 100
+    assert np.all(q[o:o + 8192] == 0); o += 8192
+    assert q[o] == np.float32(0.25); o += 1
+    for ci, co, k in ((512, 512, 3), (512, 256, 3), (256, 128, 5)):
+        n = co * ci * k * k
+        assert np.abs(q[o:o + n]).max() <= 1 / np.sqrt(ci * k * k) * (1 + 1e-6); o += n
+        assert np.all(q[o:o + co] == 0); o += co                       # weight-init.lua:70-72 zeroes the bias
+        gam = q[o:o + co]; o += co
+        assert gam.min() >= 0 and gam.max() < 1 and 0.35 < gam.mean() < 0.65   # BN gamma ~ U(0,1)
+        assert np.all(q[o:o + co] == 0); o += co                       # beta
+        assert q[o] == np.float32(0.25); o += 1
+    n = 3 * 128 * 9
+    assert np.abs(q[o:o + n]).max() <= 1 / np.sqrt(128 * 9) * (1 + 1e-6); o += n
+    assert np.all(q[o:o + 3] == 0); o += 3
+    assert o == g.nparams == 5191687
+    # two models from different seeds differ; the same seed reproduces
+    assert np.array_equal(models.create_D((3, 32, 32), True, seed=123).get_params(), p)
+    assert not np.array_equal(models.create_D((3, 32, 32), True, seed=124).get_params(), p)
+
+
+# ------------------------------------------------------------------ A1 / U13: the epoch loop
+def test_epoch_loop_tail_batches_abort_and_confusion():
+    """adversarial.lua:51-68: the loop advances B/2 examples per step, the tail batch shrinks to what is left, and fewer than 4
+    examples end the epoch; :101-106,286-291: the confusion matrix counts D's B outputs of every step and totalValid = trace/total."""
+    rng = np.random.default_rng(3)
+    g = models.create_G((3, 32, 32), 100, seed=1); d = models.create_D((3, 32, 32), True, seed=2)
+    t = adversarial.Trainer(g, d)
+    data = rng.uniform(0, 1, (40, 3, 32, 32)).astype(np.float32)
+    seen = []
+    orig = t.step
+
+    def spy(cfg, real, zD, zG):
+        seen.append((cfg.B, real.shape, zD.shape, zG.shape))
+        return orig(cfg, real, zD, zG)
+    t.step = spy
+    # N_epoch = 22, B = 8: t = 1, 5, 9, 13 -> 8 ; t = 17 -> min(8, 6) = 6 ; t = 21 -> 2 < 4 -> abort
+    acc, dt = adversarial.train(t, adversarial.Opt(batchSize=8, N_epoch=22), data, rng)
+    assert [s[0] for s in seen] == [8, 8, 8, 8, 6]
+    assert seen[-1][1] == (1, 3, 3, 32, 32) and seen[-1][2] == (1, 3, 100) and seen[-1][3] == (1, 6, 100)
+    assert 0.0 <= acc <= 1.0 and dt > 0
+    # N_epoch = 0 -> the dataset's size (adversarial.lua:30); odd tails are made even (fevalD needs B/2 real + B/2 fake)
+    seen.clear()
+    acc, _ = adversarial.train(t, adversarial.Opt(batchSize=16, N_epoch=0, D_iterations=2), data[:21], rng)
+    assert [s[0] for s in seen] == [16, 12, 4] and seen[0][1] == (2, 8, 3, 32, 32)
+    with pytest.raises(lib.CatgenError):
+        adversarial.train(t, adversarial.Opt(), data, rng, maxAccuracyD=0.9)
+    # the confusion matrix really is D's thresholded outputs against [1]*B/2 + [0]*B/2
+    seen.clear()
+    outs = []
+
+    def spy2(cfg, real, zD, zG):
+        r = orig(cfg, real, zD, zG); outs.append(r[2].copy()); return r
+    t.step = spy2
+    acc, _ = adversarial.train(t, adversarial.Opt(batchSize=8, N_epoch=8), data, rng)
+    good = sum(int((o[:len(o) // 2] > 0.5).sum() + (o[len(o) // 2:] <= 0.5).sum()) for o in outs)
+    assert acc == pytest.approx(good / sum(len(o) for o in outs))
+
+
+# ------------------------------------------------------------------ F2: checkpoint on the real models
+def test_checkpoint_round_trip_continues_training(tmp_path):
+    """train.lua:252-261 / :127-137 through catgen/checkpoint.py on GPU models: a restored pair produces the same images and takes
+    the same next step as the pair that was saved (optimiser state is not part of the reference's checkpoint either; both continue
+    with a fresh trainer)."""
+    rng = np.random.default_rng(9)
+    Cc, B = 3, 8
+    g = models.create_G((Cc, 32, 32), 100, seed=1); d = models.create_D((Cc, 32, 32), True, seed=2)
+    t = adversarial.Trainer(g, d)
+    for _ in range(3):
+        real, zD, zG, _, _ = _closure_inputs(rng, Cc, B)
+        t.step(lib.default_cfg(B), real[None], zD[None], zG[None])
+    path = str(tmp_path / "adversarial_net.npz")
+    checkpoint.save(path, g, d, epoch=7, opt={"batchSize": B, "scale": 32})
+    g2 = models.create_G((Cc, 32, 32), 100, seed=99); d2 = models.create_D((Cc, 32, 32), True, seed=98)
+    epoch, opt = checkpoint.load(path, g2, d2)
+    assert epoch == 7 and int(opt["batchSize"]) == B
+    assert np.array_equal(g2.get_params(), g.get_params()) and np.array_equal(d2.get_params(), d.get_params())
+    assert np.array_equal(g2.get_bn_running(), g.get_bn_running())
+    z = rng.uniform(-1, 1, (B, 100)).astype(np.float32)
+    g.evaluate(); g2.evaluate()
+    assert np.array_equal(g.forward(z), g2.forward(z)), "evaluate()-mode images use the restored running statistics"
+    g.training(); g2.training()
+    real, zD, zG, mD, mG = _closure_inputs(rng, Cc, B)
+    ta, tb = adversarial.Trainer(g, d), adversarial.Trainer(g2, d2)
+    d.set_masks(np.stack([mD, mG]), B, 2); d2.set_masks(np.stack([mD, mG]), B, 2)
+    ra = ta.step(lib.default_cfg(B), real[None], zD[None], zG[None])
+    rb = tb.step(lib.default_cfg(B), real[None], zD[None], zG[None])
+    assert abs(ra[0][0] - rb[0][0]) < 1e-5 and abs(ra[1][0] - rb[1][0]) < 1e-4 and np.abs(ra[2] - rb[2]).max() < 1e-5
+    with pytest.raises(ValueError):
+        checkpoint.load(path, models.create_G((Cc, 32, 32), 100, kind=lib.G32UP), d2)

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import pyoracle as po
-import torch_ref as tr
+from oracle import torch_ref as tr
 
 torch.set_num_threads(8)
 

@@ -1,7 +1,7 @@
 """How well-conditioned is G's BACKWARD pass in a real GAN step, and what does operand rounding in the backward
 convolutions do to G's parameter gradient?  Off the product path; CPU only.
 
-Truth = float64 PyTorch restatement of G (tests/torch_ref.py) back-propagating the ACTUAL image gradient that D
+Truth = float64 PyTorch restatement of G (oracle/torch_ref.py) back-propagating the ACTUAL image gradient that D
 produces for the generator update (oracle fevalG_on_D path), not random noise.  Compared against it:
   fp32            : the same graph in float32 (an honest fp32 implementation)
   tf32/fp16/bf16/fp16-scaled : float64 arithmetic, but the operands of every conv dgrad/wgrad (gy, W, x) rounded to that format
@@ -12,7 +12,7 @@ import os, sys
 import numpy as np, torch, torch.nn.functional as F
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [R, os.path.join(R, "tests")]
 from oracle import pyoracle as po
-import torch_ref as tr
+from oracle import torch_ref as tr
 torch.set_num_threads(8)
 
 def rn_tf32(x):

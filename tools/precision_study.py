@@ -4,7 +4,7 @@ Off the product path.  Result of the run that fixed the precision choice is in p
 import sys, time, numpy as np, torch, torch.nn.functional as F
 import os; R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [R, os.path.join(R, "tests")]
 from oracle import pyoracle as po
-import torch_ref as tr
+from oracle import torch_ref as tr
 torch.set_num_threads(8)
 def rn_tf32(x):
     i = x.contiguous().view(torch.int32)

@@ -72,7 +72,15 @@ __global__ void __launch_bounds__(256) k_parts_to_torch_acc(const float* __restr
     float sum = 0.f;
     if (ci < Ci && co < Co) {
       const float* src = part + ((long)tap * Ci + ci) * Co + co;
-      for (int z = 0; z < Z; ++z) sum += src[(long)z * zstride];
+      // four independent chains keep four loads in flight per thread (a single chain walked Z loads megabytes apart serially:
+      // 5.2 ms in round 1); the association ((s0+s1)+(s2+s3)) is fixed, so the result is deterministic
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int z = 0;
+      for (; z + 4 <= Z; z += 4) {
+        s0 += src[(long)z * zstride]; s1 += src[(long)(z + 1) * zstride]; s2 += src[(long)(z + 2) * zstride]; s3 += src[(long)(z + 3) * zstride];
+      }
+      for (; z < Z; ++z) s0 += src[(long)z * zstride];
+      sum = (s0 + s1) + (s2 + s3);
     }
     t[(tap * CIB + cil) * 33 + col] = sum;
   }
@@ -84,9 +92,8 @@ __global__ void __launch_bounds__(256) k_parts_to_torch_acc(const float* __restr
     if (ci < Ci && co < Co) gW[((long)co * Ci + ci) * kk + tap] += t[(tap * CIB + cil) * 33 + col];   // accGradParameters adds
   }
 }
-// NOTE (measured): calling this with Z > 1 made it the slowest kernel of the step (5.2 ms): with ~128 blocks each thread walked
-// ~275 partial-sum loads megabytes apart, serially.  Callers therefore reduce the partials first with the fully parallel
-// element-wise kernels (k_sum_parts / k_splitk_reduce) and use this kernel with Z = 1 for the layout change only.
+// Z > 1: the split partials are summed here as well (round 1 needed a separate k_sum_parts pass first because a single dependent
+// chain per thread made this kernel 5.2 ms; see the loop above).
 int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk) {
   int CIB = kk <= 9 ? 8 : (kk <= 25 ? 4 : 2);     // smaller channel blocks for big filters: more blocks, runs of >= 98 floats
   if (kk * CIB * 33 > 6600) return CG_ERR_UNSUPPORTED;

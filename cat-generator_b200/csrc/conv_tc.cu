@@ -214,7 +214,28 @@ __global__ void k_pack_wslices(const float* __restrict__ Wp, uint8_t* __restrict
 __device__ __forceinline__ void pack_slices_job(const float* __restrict__ W, uint8_t* __restrict__ Wq, const ConvSpec& s, int dgrad, int CB, long tid, long nthreads) {
   const int k = s.k, kk = k * k;
   const int Cin = dgrad ? s.Co : s.Ci, Cout = dgrad ? s.Ci : s.Co;         // the forward conv this operand feeds: Cin -> Cout
-  const int Cip = ((Cin + 63) / 64) * 64, Cop = ((Cout + 15) / 16) * 16, nsub = CB / 64;
+  const int Cop = ((Cout + 15) / 16) * 16;
+  if (CB == 32) {   // k_conv_ps: 32-channel slices in stream order [cb][tap][4 planes][Cop][8], only the blocks that hold data
+    const int ncb = (Cin + 31) / 32;
+    const long nchunks = (long)kk * ncb * 4 * Cop;
+    for (long i = tid; i < nchunks; i += nthreads) {
+      int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 4); t /= 4; int tap = (int)(t % kk); int cb = (int)(t / kk);
+      int ci0 = cb * 32 + c * 8;
+      int ky = tap / k, kx = tap % k; if (dgrad) { ky = k - 1 - ky; kx = k - 1 - kx; }
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int ci = ci0 + j;
+        v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, 1, 1, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
+      }
+      uint4 out; uint32_t* o = &out.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); o[j] = *reinterpret_cast<uint32_t*>(&h); }
+      reinterpret_cast<uint4*>(Wq)[i] = out;
+    }
+    return;
+  }
+  const int Cip = ((Cin + 63) / 64) * 64, nsub = CB / 64;
   const long nchunks = (long)kk * Cip * Cop / 8;
   for (long i = tid; i < nchunks; i += nthreads) {
     int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 8); t /= 8; int sub = (int)(t % nsub); t /= nsub; int tap = (int)(t % kk); int cb = (int)(t / kk);
@@ -541,8 +562,10 @@ struct WSliceEntry { const uint8_t* wq; int CB; };
 static std::unordered_map<const float*, WSliceEntry>& wslice_registry() { static std::unordered_map<const float*, WSliceEntry> r; return r; }
 void conv_tc_register_wslices(const float* key, const uint8_t* wq, int CB) { wslice_registry()[key] = WSliceEntry{wq, CB}; }
 void conv_tc_unregister_wslices(const float* key) { wslice_registry().erase(key); }
+static bool conv_v1();
 bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
   if (!(k == 3 || k == 5 || k == 7)) return false;
+  if (!conv_v1()) { *CB = 32; *bytes = (size_t)k * k * ((Cin + 31) / 32) * 32 * (((Cout + 15) / 16) * 16) * 2; return true; }
   const int Ci = ((Cin + 63) / 64) * 64, Co = ((Cout + 15) / 16) * 16;
   int NB, TL; tc_plan<2>(Ci, Co, k, 2, &NB, &TL, CB);
   *bytes = (size_t)k * k * Ci * Co * 2;
@@ -550,22 +573,34 @@ bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
 }
 
 // ====================================================================================================================
-// EXPERIMENT FOR ROUND 2 -- OFF BY DEFAULT (CATGEN_TC_TL4=1 selects it for fp16 runs).  Written without a GPU; run ONCE at the very end of
-// round 1: the op-level conv parity tests pass with it and G conv3 fprop took 194 us instead of 234, dgrad 206 instead of 227
-// (profiles/r01_conv3_tl4_experiment.txt).  The model-level suite has not been run with it, hence not the default yet.
-// Four tiles per CTA instead of two, so that every weight slice fetched from L2 feeds 512 pixels instead of 256.
-// Why: DESIGN.md section 4.1 -- with two 128-wide tiles a CTA has to take in 18.8 KB per 512 cycles of MMA work (36.7 B/cycle/SM)
-// and gets 23.5; the main loop waits a quarter of its time for weights whatever the ring depth.  With four tiles (all 512 TMEM
-// columns at N = 128) and 32-channel blocks (so that 2 x 4 patch buffers still fit) the same 512 cycles need 8 KB of weights +
-// 2.5 KB of patches = 20.5 B/cycle/SM.  If the hypothesis is right, conv3 fprop goes from ~235 us towards ~150 us; if the time
-// does not move, the hypothesis is wrong and the CTA-pair kernel (tools/tc_pair_probe.cu) is not the fix either.
-// Same operands, barriers and epilogue as k_conv_tc<2>; differences: TL = 4, slices of 32 channels (two MMAs per tile and
-// slice), issuer warp 6 owns tiles 0-1 and warp 7 tiles 2-3.  Parity: run tests/test_gpu_parity.py with CATGEN_TC_TL4=1.
-struct Tc4Params {
+// k_conv_ps -- the forward-conv engine of round 2: PERSISTENT CTAs, FOUR accumulator slots in TMEM on a STAGGERED schedule.
+//
+// What round 1 measured on k_conv_tc (profiles/r01_conv3_cta_timeline*.txt, r01_ncu_conv3_v3.txt): with two 128-pixel tiles per CTA the
+// issue loop waits a quarter of its time for weight slices (every weight byte fetched from L2 feeds only 256 pixels: 965 MB over the
+// crossbar per conv3 launch against 154 MB algorithmic), the epilogue (10.6k of 93k cycles) overlaps nothing, and 512 CTAs on 148 SMs
+// run 3.46 waves.  This kernel changes all three:
+//   * one CTA per SM loops over its tiles (tile t = blockIdx.x + i * gridDim.x): no wave quantisation, one prologue;
+//   * FOUR tiles accumulate side by side (4 x NB <= 512 TMEM columns) and share every weight slice: a slice fetched once feeds 512
+//     pixels (the round-1 TL4 experiment, 234 -> 194 us on conv3, profiles/r01_conv3_tl4_experiment.txt);
+//   * the four slots do not run in lockstep: the weight stream is CYCLIC (slice g mod nslices) and a tile may start its K loop at any
+//     slice -- it ends one full cycle later.  Slot j starts its k-th tile at slice j*D + k*(nslices + D), so the slots finish D slices
+//     apart and each slot's epilogue (TMEM -> registers -> shared-memory staging -> 128-byte lines) drains while the other three keep
+//     the tensor pipe busy; the slot rejoins the stream D slices after it ended.  The schedule is static: every role computes it.
+// Roles (320 threads): warps 0-3 epilogue (TMEM lane quarters) ; warps 4-7 MMA issuers, one per slot (one thread retires an MMA per
+// ~84 cycles, tools/tc_rate.cu, so N = 64 layers need more than two) ; warp 8 streams weight slices (32 channels x NB columns, one
+// bulk copy) ; warp 9 loads patches (one tiled TMA per slot and 32-channel block, issued in the order the buffers free up).
+// Operand layouts are k_conv_tc's (halo'd patch resident in shared memory, a filter tap = a shifted descriptor start address).
+constexpr int PS_SLOTS = 4;
+struct PsParams {
   const uint8_t *xq, *wq; const float *bias, *scale2; float* y;
-  int N, H, W, Ci, Co, Cor, k, p, Hq, Wq, ncb, tiles_x, tiles_y, NB, S, ntiles;
+  float inv_host;                      // epilogue factor on the accumulator (1 unless the weights were packed pre-scaled)
+  int N, H, W, Co, Cor, k, p;          // Co: padded column count of the slices (multiple of 16); Cor: real Cout = row stride of y
+  int ncb, kk, nslices;                // 32-channel blocks that hold data, taps, ncb * kk
+  int tiles_x, tiles_y, ntiles;
+  int NB, S, D;                        // columns per CTA, weight ring depth, stagger / gap in slices
   uint32_t patch_bytes, slice_bytes;
 };
+// Weights Wp[(tap,ci)][co] fp32 -> 32-channel slices in stream order Wq[cb][tap][c 0..3][Cop][8 fp16]; zero beyond Ci / Co.
 __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int Cop, int kk) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
     int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 4); t /= 4; int tap = (int)(t % kk); int cb = (int)(t / kk);
@@ -579,32 +614,36 @@ __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restri
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
 }
-__global__ void __launch_bounds__(256, 1) k_conv_tc4(Tc4Params P, const __grid_constant__ CUtensorMap tmx) {
-  constexpr int TLX = 4, PLX = 4;                           // tiles per CTA; 16-byte channel planes per 32-channel block / slice
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+
+__global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_pfull[2], bar_pempty[2], bar_wfull[16], bar_wempty[16], bar_acc;
+  __shared__ __align__(8) uint64_t bar_wfull[16], bar_wempty[16], bar_pfull[PS_SLOTS][2], bar_pempty[PS_SLOTS][2], bar_acc[PS_SLOTS], bar_tfree[PS_SLOTS];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* patch0 = smem;                                    // patch buffers [2][TLX]
-  uint8_t* wring = smem + 2 * (size_t)TLX * P.patch_bytes;   // S weight slices
-  const int tile0 = blockIdx.x * TLX;
-  const int ntl = (P.ntiles - tile0) < TLX ? (P.ntiles - tile0) : TLX;
-  auto tile_xy = [&](int tl, int& n, int& y0, int& x0) {
-    int t = tile0 + tl; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
-  };
-  const int co0 = blockIdx.y * P.NB;
+  uint8_t* patch0 = smem;                                              // [slot][buffer] patches
+  uint8_t* wring = smem + (size_t)2 * PS_SLOTS * P.patch_bytes;        // S weight slices
+  float* stage0 = reinterpret_cast<float*>(wring + (size_t)P.S * P.slice_bytes);   // epilogue staging, 4 warps x 32 rows x 36 floats
+
+  const int gx = gridDim.x, co0 = blockIdx.y * P.NB;
+  const int nt = (P.ntiles - (int)blockIdx.x + gx - 1) / gx;           // tiles of this CTA (>= 1: the host keeps gridDim.x <= ntiles)
+  const int ns = P.nslices, D = P.D, kk = P.kk, ncb = P.ncb;
+  // slot j owns tiles j, j+4, ...; its k-th tile is accumulated over slices [j*D + k*(ns+D), +ns)
+  int total_g = 0;
+#pragma unroll
+  for (int j = 0; j < PS_SLOTS; ++j) { int nk = (nt - j + PS_SLOTS - 1) / PS_SLOTS; if (nk > 0) { int e = j * D + (nk - 1) * (ns + D) + ns; total_g = e > total_g ? e : total_g; } }
   const int Hp = 16 + 2 * P.p, Wp = 8 + 2 * P.p;
   const uint32_t plane_bytes = (uint32_t)Hp * Wp * 16;
-  const int kk = P.k * P.k;
-  const int nslices = P.ncb * kk;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 2); }
-    for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 2); }
-    mbar_init(&bar_acc, 2);
+    for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], PS_SLOTS); }
+    for (int j = 0; j < PS_SLOTS; ++j) {
+      for (int b = 0; b < 2; ++b) { mbar_init(&bar_pfull[j][b], 1); mbar_init(&bar_pempty[j][b], 1); }
+      mbar_init(&bar_acc[j], 1); mbar_init(&bar_tfree[j], 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  int ncols = 32; while (ncols < TLX * P.NB) ncols <<= 1;
+  int ncols = 32; while (ncols < PS_SLOTS * P.NB) ncols <<= 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -613,159 +652,248 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc4(Tc4Params P, const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base_s;
+  auto tile_xy = [&](int i, int& n, int& y0, int& x0) {
+    int t = (int)blockIdx.x + i * gx; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
+  };
 
-  if (warp == 4) {
-    if (lane == 0) {   // weight slices [slice][c 0..3][Co][16 B]
-      int st = 0; uint32_t ph = 0;
-      for (int s = 0; s < nslices; ++s, st = (st + 1 == P.S) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
+  if (warp == 8) {
+    // ===== weight producer: the cyclic slice stream, one bulk copy per slice (one per plane when the CTA owns a column block)
+    if (lane == 0) {
+      int st = 0, s = 0; uint32_t ph = 0;
+      for (int g = 0; g < total_g; ++g) {
         mbar_wait(&bar_wempty[st], ph ^ 1);
         mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
         uint8_t* dst = wring + (size_t)st * P.slice_bytes;
-        const uint8_t* src = P.wq + (size_t)s * PLX * P.Co * 16;
+        const uint8_t* src = P.wq + (size_t)s * 4 * P.Co * 16;
         if (P.NB == P.Co) bulk_g2s(dst, src, P.slice_bytes, &bar_wfull[st]);
-        else for (int c = 0; c < PLX; ++c) bulk_g2s(dst + (size_t)c * P.NB * 16, src + ((size_t)c * P.Co + co0) * 16, P.NB * 16, &bar_wfull[st]);
+        else for (int c = 0; c < 4; ++c) bulk_g2s(dst + (size_t)c * P.NB * 16, src + ((size_t)c * P.Co + co0) * 16, P.NB * 16, &bar_wfull[st]);
+        if (++s == ns) s = 0;
+        if (++st == P.S) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 5) {
-    if (lane == 0) {   // patches: one tiled TMA per tile and 32-channel block
-      for (int cb = 0; cb < P.ncb; ++cb) {
-        int buf = cb & 1; uint32_t ph = (cb >> 1) & 1;
-        mbar_wait(&bar_pempty[buf], ph ^ 1);
-        mbar_expect_tx(&bar_pfull[buf], (uint32_t)ntl * P.patch_bytes);
-        for (int tl = 0; tl < ntl; ++tl) {
-          int n, y0, x0; tile_xy(tl, n, y0, x0);
-          tma_patch_4d(patch0 + (size_t)(buf * TLX + tl) * P.patch_bytes, &tmx, x0 * 8, y0, cb * PLX, n, &bar_pfull[buf]);
-        }
+  } else if (warp == 9) {
+    // ===== patch producer.  Per slot a stream of segments (= one 32-channel block of one tile resident in one of the slot's two
+    // buffers); segment c of a slot may be loaded once segment c-2 has been consumed.  Loads are issued in the order in which
+    // their buffers free up (4-way merge on that slice index), so waiting on one slot never holds back a load another slot needs first.
+    if (lane == 0) {
+      int kj[PS_SLOTS], qj[PS_SLOTS], cj[PS_SLOTS], gj[PS_SLOTS], e1[PS_SLOTS], e2[PS_SLOTS], nkj[PS_SLOTS];
+#pragma unroll
+      for (int j = 0; j < PS_SLOTS; ++j) { kj[j] = 0; qj[j] = 0; cj[j] = 0; gj[j] = j * D; e1[j] = -1; e2[j] = -1; nkj[j] = (nt - j + PS_SLOTS - 1) / PS_SLOTS; if (nkj[j] < 0) nkj[j] = 0; }
+      for (;;) {
+        int best = -1, bestr = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < PS_SLOTS; ++j) if (kj[j] < nkj[j] && e2[j] < bestr) { bestr = e2[j]; best = j; }
+        if (best < 0) break;
+        const int j = best;
+        // tile kj of slot j starts at slice gstart; segment qj covers [gj, gj + len)
+        const int gstart = j * D + kj[j] * (ns + D);
+        const int s0 = gstart % ns, cb0 = s0 / kk, tap0 = s0 - cb0 * kk;
+        const int nseg = ncb == 1 ? 1 : ncb + (tap0 > 0 ? 1 : 0);
+        int cb, len;
+        if (ncb == 1) { cb = 0; len = ns; }
+        else if (qj[j] == 0) { cb = cb0; len = kk - tap0; }
+        else { cb = cb0 + qj[j]; if (cb >= ncb) cb -= ncb; len = (qj[j] == nseg - 1 && tap0 > 0) ? tap0 : kk; }
+        const int buf = cj[j] & 1; const uint32_t ph = (uint32_t)(cj[j] >> 1) & 1u;
+        mbar_wait(&bar_pempty[j][buf], ph ^ 1);
+        mbar_expect_tx(&bar_pfull[j][buf], P.patch_bytes);
+        int n, y0, x0; tile_xy(j + PS_SLOTS * kj[j], n, y0, x0);
+        tma_patch_4d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, &bar_pfull[j][buf]);
+        e2[j] = e1[j]; e1[j] = gj[j] + len; gj[j] += len; cj[j]++;
+        if (++qj[j] == nseg) { qj[j] = 0; kj[j]++; gj[j] = j * D + kj[j] * (ns + D); }
       }
     }
-  } else if (warp == 6 || warp == 7) {
-    if (lane == 0) {   // two issuers, two tiles each; per slice and tile: two MMAs (32 channels = 2 x K 16)
-      const int me = warp - 6;
+  } else if (warp >= 4 && warp < 8) {
+    // ===== MMA issuer of slot j = warp - 4.  EVERY issuer walks the whole slice stream and arrives on every slice's "empty"
+    // barrier (count 4) -- with a commit behind its MMAs while its slot is accumulating, with a plain arrive otherwise.
+    if (lane == 0) {
+      const int j = warp - 4;
+      const int nk = (nt - j + PS_SLOTS - 1) / PS_SLOTS;
       const uint32_t idesc = (1u << 4) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t b_lbo = (uint32_t)P.NB * 16;
       const uint32_t a_hi = desc_hi((uint32_t)Wp * 16), b_hi = desc_hi(128);
-      const uint32_t plane16 = plane_bytes >> 4, patch16 = P.patch_bytes >> 4, slice16 = P.slice_bytes >> 4;
+      const uint32_t plane16 = plane_bytes >> 4, slice16 = P.slice_bytes >> 4;
       const uint32_t a_kstep = 2 * plane16, b_kstep = 2 * (b_lbo >> 4);
       const uint32_t w_lo0 = desc_lo(smem_u32(wring), b_lbo);
-      const int S = P.S, k = P.k, NB = P.NB;
-      uint32_t st = 0, wph = 0, acc0 = 0;
-      for (int cb = 0; cb < P.ncb; ++cb) {
-        const int buf = cb & 1;
-        mbar_wait(&bar_pfull[buf], (cb >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t p_lo0 = desc_lo(smem_u32(patch0 + (size_t)(buf * TLX) * P.patch_bytes), plane_bytes);
-        uint32_t row_lo = p_lo0;
-        for (int ky = 0; ky < k; ++ky, row_lo += (uint32_t)Wp) {
-          for (int kx = 0; kx < k; ++kx) {
-            const uint32_t a_lo = row_lo + (uint32_t)kx;
-            mbar_wait(&bar_wfull[st], wph);
+      const uint32_t p_lo_buf0 = desc_lo(smem_u32(patch0 + (size_t)(j * 2) * P.patch_bytes), plane_bytes), patch16 = P.patch_bytes >> 4;
+      const uint32_t tm = tmem + (uint32_t)(j * P.NB);
+      const int S = P.S, k = P.k;
+      uint32_t st = 0, wph = 0, acc = 0;
+      int kt = 0, g0 = j * D, seg = 0;
+      int tap = 0, ky = 0, kx = 0;
+      uint32_t p_lo = p_lo_buf0;
+      for (int g = 0; g < total_g; ++g) {
+        mbar_wait(&bar_wfull[st], wph);
+        if (kt < nk && g >= g0) {                           // g < g0 + ns holds by construction (the window is closed below)
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          if (g == g0) {
+            if (kt > 0) { mbar_wait(&bar_tfree[j], (uint32_t)(kt - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;"); }   // epilogue has drained this slot's previous tile
+            const int s0 = g0 % ns; const int cb0 = s0 / kk; tap = s0 - cb0 * kk; ky = tap / k; kx = tap - ky * k;
+            mbar_wait(&bar_pfull[j][seg & 1], (uint32_t)(seg >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t w_lo = w_lo0 + st * slice16;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int tl = 2 * me + j;
-              if (tl < ntl) {
-                const uint32_t at = a_lo + (uint32_t)tl * patch16, tm = tmem + (uint32_t)(tl * NB);
-                umma<2>(tm, desc64(at, a_hi), desc64(w_lo, b_hi), idesc, acc0);
-                umma<2>(tm, desc64(at + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
-              }
-            }
-            acc0 = 1u;
-            umma_commit(&bar_wempty[st]);
-            if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
+            p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
+            acc = 0;
+          } else if (tap == 0 && ncb > 1) {                 // next 32-channel block: hand the buffer back, take the other one
+            umma_commit(&bar_pempty[j][seg & 1]); ++seg;
+            mbar_wait(&bar_pfull[j][seg & 1], (uint32_t)(seg >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
           }
-        }
-        umma_commit(&bar_pempty[buf]);
+          const uint32_t a_lo = p_lo + (uint32_t)(ky * Wp + kx), w_lo = w_lo0 + st * slice16;
+          umma<2>(tm, desc64(a_lo, a_hi), desc64(w_lo, b_hi), idesc, acc);
+          umma<2>(tm, desc64(a_lo + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+          acc = 1u;
+          if (++kx == k) { kx = 0; ++ky; }
+          if (++tap == kk) { tap = 0; ky = 0; kx = 0; }
+          if (g == g0 + ns - 1) {                           // the tile's K cycle is complete
+            umma_commit(&bar_pempty[j][seg & 1]); ++seg;
+            umma_commit(&bar_acc[j]);
+            ++kt; g0 += ns + D;
+          }
+          umma_commit(&bar_wempty[st]);                     // arrives when the MMAs reading this slice have retired
+        } else mbar_arrive(&bar_wempty[st]);
+        if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
       }
-      umma_commit(&bar_acc);
     }
-  }
-
-  if (warp < 4) {   // epilogue as in k_conv_tc: staged through shared memory for full-width blocks, per-lane stores otherwise
-    mbar_wait(&bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;");
+  } else {
+    // ===== epilogue (warps 0-3): tiles in completion order (k, j); warp w owns TMEM lanes 32w..32w+31 = pixels of the tile
     const int m = warp * 32 + lane;
     const bool vec = (P.Cor & 3) == 0;
-    const float inv = P.scale2 ? P.scale2[1] : 1.f;
-    float* stage = reinterpret_cast<float*>(patch0) + warp * (32 * 36);
+    const float inv = (P.scale2 ? P.scale2[1] : 1.f) * P.inv_host;
+    float* stage = stage0 + warp * (32 * 36);
     const bool wide = vec && (P.NB & 31) == 0;
-    for (int tl = 0; tl < ntl; ++tl) {
-      int n, y0, x0; tile_xy(tl, n, y0, x0);
-      for (int c0 = 0; c0 < P.NB; c0 += 16) {
-        uint32_t v[16];
-        uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * P.NB + c0);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;");
-        if (wide && co0 + c0 + 16 <= P.Cor) {
+    for (int i = 0; i < nt; ++i) {
+      const int j = i & (PS_SLOTS - 1), kt = i >> 2;
+      mbar_wait(&bar_acc[j], (uint32_t)kt & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      int n, y0, x0; tile_xy(i, n, y0, x0);
+      const uint32_t tcol = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * P.NB);
+      if (wide) {
+        for (int c0 = 0; c0 < P.NB; c0 += 32) {
+          uint32_t v[32];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                       : "r"(tcol + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;");
+          if (co0 + c0 + 32 <= P.Cor) {                    // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co0 + c0 + j] : 0.f);
-            o.y = __uint_as_float(v[j + 1]) * inv + (P.bias ? P.bias[co0 + c0 + j + 1] : 0.f);
-            o.z = __uint_as_float(v[j + 2]) * inv + (P.bias ? P.bias[co0 + c0 + j + 2] : 0.f);
-            o.w = __uint_as_float(v[j + 3]) * inv + (P.bias ? P.bias[co0 + c0 + j + 3] : 0.f);
-            *reinterpret_cast<float4*>(stage + lane * 20 + j) = o;          // 16 + 4 pad floats per pixel row
-          }
-          __syncwarp();
-          const int q = (lane & 3) * 4;                                       // 4 lanes per pixel (64 bytes), 8 pixels per store
+            for (int q = 0; q < 32; q += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co0 + c0 + q] : 0.f);
+              o.y = __uint_as_float(v[q + 1]) * inv + (P.bias ? P.bias[co0 + c0 + q + 1] : 0.f);
+              o.z = __uint_as_float(v[q + 2]) * inv + (P.bias ? P.bias[co0 + c0 + q + 2] : 0.f);
+              o.w = __uint_as_float(v[q + 3]) * inv + (P.bias ? P.bias[co0 + c0 + q + 3] : 0.f);
+              *reinterpret_cast<float4*>(stage + lane * 36 + q) = o;
+            }
+            __syncwarp();
+            const int q4 = (lane & 7) * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int pl = i * 8 + (lane >> 2), mm = warp * 32 + pl;
-            const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
-            float4 o = *reinterpret_cast<const float4*>(stage + pl * 20 + q);
-            if (oy < P.H && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q) = o;
+            for (int r = 0; r < 8; ++r) {                   // 8 lanes per pixel: whole 128-byte lines leave the SM
+              const int pl = r * 4 + (lane >> 3), mm = warp * 32 + pl;
+              const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+              float4 o = *reinterpret_cast<const float4*>(stage + pl * 36 + q4);
+              if (oy < P.H && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q4) = o;
+            }
+            __syncwarp();
+          } else {                                          // padded columns past Cout
+            const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+            if (oy < P.H && ox < P.W) {
+              float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+              for (int q = 0; q < 32; ++q) { int co = co0 + c0 + q; if (co < P.Cor) out[c0 + q] = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co] : 0.f); }
+            }
           }
-          __syncwarp();
-        } else {
-          const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-          if (oy < P.H && ox < P.W) {
-            float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
-            for (int j = 0; j < 16; ++j) { int co = co0 + c0 + j; if (co < P.Cor) out[c0 + j] = __uint_as_float(v[j]) * inv + (P.bias ? P.bias[co] : 0.f); }
+        }
+      } else {
+        const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+        const bool valid = oy < P.H && ox < P.W;
+        float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+        for (int c0 = 0; c0 < P.NB; c0 += 16) {
+          uint32_t v[16];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "r"(tcol + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;");
+          if (valid && vec && co0 + c0 + 16 <= P.Cor) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co0 + c0 + q] : 0.f);
+              o.y = __uint_as_float(v[q + 1]) * inv + (P.bias ? P.bias[co0 + c0 + q + 1] : 0.f);
+              o.z = __uint_as_float(v[q + 2]) * inv + (P.bias ? P.bias[co0 + c0 + q + 2] : 0.f);
+              o.w = __uint_as_float(v[q + 3]) * inv + (P.bias ? P.bias[co0 + c0 + q + 3] : 0.f);
+              *reinterpret_cast<float4*>(out + c0 + q) = o;
+            }
+          } else if (valid) {                               // ragged Cout (1, 3): only the real columns exist in y
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { int co = co0 + c0 + q; if (co < P.Cor) out[c0 + q] = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co] : 0.f); }
           }
         }
       }
+      // the slot's columns may be overwritten by its next tile
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tfree[j]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
 }
-static int conv_tc4_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
-                        const uint8_t* xq_prepacked) {
-  const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // same operand padding as conv_tc_run<2>: the packed activations are shared
+
+static bool conv_v1() { static const bool v = getenv("CATGEN_CONV_V1") != nullptr; return v; }   // the round-1 kernel, kept for A/B measurements
+
+static int conv_ps_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
+                       const uint8_t* xq_prepacked) {
+  const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // operand padding of the packed activations (shared with the weight gradient)
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
-  int NB = Co > 128 ? 128 : Co; while (NB >= 16 && Co % NB) NB -= 16;       // four accumulators of NB columns must fit 512 TMEM columns
+  int NB = Co > 128 ? 128 : Co; while (NB >= 16 && Co % NB) NB -= 16;
   if (NB < 16) return CG_ERR_UNSUPPORTED;
-  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * NB * 16;
-  if (8 * patch_bytes + 3 * slice_bytes > 216 * 1024) return CG_ERR_UNSUPPORTED;
-  int S = (int)((216 * 1024 - 8 * patch_bytes) / slice_bytes); if (S > 16) S = 16;
+  const int ncb = (Cir + 31) / 32;
+  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * NB * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
+  const size_t budget = 226 * 1024;
+  if (2 * PS_SLOTS * patch_bytes + stage_bytes + 3 * slice_bytes > budget) return CG_ERR_UNSUPPORTED;
+  int S = (int)((budget - 2 * PS_SLOTS * patch_bytes - stage_bytes) / slice_bytes); if (S > 16) S = 16;
   const int ntiles = N * (W / 8) * ((H + 15) / 16);
-  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, wq_bytes = (size_t)kk * Ci * Co * 2;
-  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255)) + wq_bytes + 512);
+  size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, wq_bytes = (size_t)kk * ncb * 32 * Co * 2;
+  const uint8_t* wq_cached = nullptr;
+  { auto it = wslice_registry().find(Wp); if (it != wslice_registry().end() && it->second.CB == 32) wq_cached = it->second.wq; }
+  uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255)) + (wq_cached ? 0 : wq_bytes) + 512);
   if (!ws) return CG_ERR_CUDA;
   const uint8_t* xq = xq_prepacked ? xq_prepacked : ws;
-  uint8_t* wq = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
+  const uint8_t* wq = wq_cached;
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
-  if (!xq_prepacked) CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2);
-  CG_LAUNCH(k_pack_wslices32, grid1d(nw, 256), 256, 0, Wp, wq, nw, Cir, Cor, Co, kk);
-  Tc4Params P{};
-  P.xq = xq; P.wq = wq; P.bias = bias; P.scale2 = scale2; P.y = y;
-  P.N = N; P.H = H; P.W = W; P.Ci = Ci; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p; P.Hq = Hq; P.Wq = Wq;
-  P.ncb = Ci / 32; P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.NB = NB; P.S = S; P.ntiles = ntiles;
+  if (!xq_prepacked) { ctx().next_bytes = 4.0 * N * H * W * Cir + (double)xq_bytes; CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2); }
+  if (!wq_cached) {
+    uint8_t* wqb = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
+    CG_LAUNCH(k_pack_wslices32, grid1d(nw, 256), 256, 0, Wp, wqb, nw, Cir, Cor, Co, kk);
+    wq = wqb;
+  }
+  PsParams P{};
+  P.xq = xq; P.wq = wq; P.bias = bias; P.scale2 = scale2; P.y = y; P.inv_host = 1.f;
+  P.N = N; P.H = H; P.W = W; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p;
+  P.ncb = ncb; P.kk = kk; P.nslices = ncb * kk;
+  P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.ntiles = ntiles; P.NB = NB; P.S = S;
+  static const int d_env = getenv("CATGEN_PS_D") ? atoi(getenv("CATGEN_PS_D")) : 16;
+  P.D = d_env < 1 ? 1 : d_env;
+  if (P.D > P.nslices / 4) P.D = P.nslices / 4 > 0 ? P.nslices / 4 : 1;   // short K loops: keep the four slots overlapping (stagger < a quarter cycle)
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
-  size_t smem = 8 * patch_bytes + (size_t)S * slice_bytes;
+  const size_t smem = 2 * PS_SLOTS * patch_bytes + (size_t)S * slice_bytes + stage_bytes;
   static bool attr_done = false;
-  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
-  dim3 grid((ntiles + 3) / 4, Co / NB);
-  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;
+  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  const int gy = Co / NB;
+  int gx = ctx().sm_count / gy; if (gx < 1) gx = 1;
+  const int want = (ntiles + PS_SLOTS - 1) / PS_SLOTS;                     // every CTA should own four tiles (they share each weight slice)
+  if (gx > want) gx = want;
+  dim3 grid(gx, gy);
+  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;             // algorithmic (unpadded) work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
-  CG_LAUNCH(k_conv_tc4, grid, 256, smem, P, tmx);
+  CG_LAUNCH(k_conv_ps, grid, 320, smem, P, tmx);
   return CG_OK;
 }
 // ====================================================================================================================
@@ -773,10 +901,7 @@ static int conv_tc4_run(const float* x, const float* Wp, const float* bias, floa
 template <int ES>
 static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
                        const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
-  if (ES == 2) {   // round-2 experiment (see k_conv_tc4)
-    static const bool tl4 = getenv("CATGEN_TC_TL4") != nullptr;
-    if (tl4) { int s4 = conv_tc4_run(x, Wp, bias, y, N, H, W, Cir, Cor, k, scale2, xq_prepacked); if (s4 != CG_ERR_UNSUPPORTED) return s4; }
-  }
+  if (ES == 2 && !conv_v1()) { int s4 = conv_ps_run(x, Wp, bias, y, N, H, W, Cir, Cor, k, scale2, xq_prepacked); if (s4 != CG_ERR_UNSUPPORTED) return s4; }
   constexpr int PER = 16 / ES, KB = 128 / ES;
   const int Ci = ((Cir + KB - 1) / KB) * KB, Co = ((Cor + 15) / 16) * 16;   // padded sizes the kernel iterates over
   const int p = (k - 1) / 2, kk = k * k;
@@ -1191,8 +1316,9 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
   CG_LAUNCH(k_wgrad_tc, grid, 256, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
-  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // fully parallel, fixed z order
-  if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; }   // layout change only
+  // straight into the Torch-layout gradient: split sum (fixed order) + layout change + accumulate in ONE kernel
+  if (gW_acc && parts_to_torch_acc(part, Z, nW, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; return CG_OK; }
+  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // packed result wanted (op-level entry points, Linear)
   return CG_OK;
 }
 

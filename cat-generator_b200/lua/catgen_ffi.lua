@@ -21,6 +21,7 @@ int cg_model_nparams(const cg_model* m, int64_t* n);
 int cg_model_get_params(cg_model* m, float* host); int cg_model_set_params(cg_model* m, const float* host);
 int cg_model_get_grads(cg_model* m, float* host); int cg_model_zero_grads(cg_model* m);
 int cg_model_set_mode(cg_model* m, int training);
+int cg_model_bn_running_len(const cg_model* m, int64_t* n); int cg_model_get_bn_running(cg_model* m, float* host); int cg_model_set_bn_running(cg_model* m, const float* host);
 int cg_G_forward(cg_model* g, const float* z, int B, float* out); int cg_G_backward(cg_model* g, const float* gout, float* gz);
 int cg_D_forward(cg_model* d, const float* x, int B, float* out_sig, float* out_pre); int cg_D_backward(cg_model* d, const float* gout, float* gx);
 int cg_bce(const float* p, const float* t, int n, float* loss, float* g);
@@ -29,6 +30,7 @@ int cg_trainer_create(cg_trainer** out, cg_model* G, cg_model* D); int cg_traine
 int cg_adam_step(cg_trainer* t, int which, const cg_step_cfg* cfg);
 int cg_train_step(cg_trainer* t, const cg_step_cfg* cfg, const float* real, const float* zD, const float* zG, float* lossD, float* lossG, float* d_out);
 int cg_dist_unique_id(char id_out[128]); int cg_dist_init(int rank, int world, const char id[128]);
+int cg_dist_set_sync_bn(int on); int cg_dist_get_sync_bn(void); int cg_dist_world(void);
 int cg_leakyrelu_fwd(const float* x, float slope, float* y, int64_t n); int cg_leakyrelu_bwd(const float* x, const float* gy, float slope, float* gx, int64_t n);
 int cg_conv_upsample_fwd(const float* x, const float* W, const float* b, float* y, int N, int Ci, int H, int Wd, int nOut, int k, int f);
 int cg_conv_upsample_bwd(const float* x, const float* gy, const float* W, float* gx, float* gW, float* gb, int N, int Ci, int H, int Wd, int nOut, int k, int f);

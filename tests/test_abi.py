@@ -99,3 +99,36 @@ def test_lua_cdef_matches_the_header():
     for root, _, files in os.walk(os.path.join(lib.PKG_DIR, "lua")):
         for f in files:
             assert "NOT EXECUTED" in open(os.path.join(root, f)).read(), f
+
+
+def test_lua_surface_covers_what_train_lua_calls():
+    """The Lua layer cannot run here; what CAN be checked is that every method the reference's train.lua / adversarial.lua /
+    utils/nn_utils.lua invoke on MODEL_G / MODEL_D, every NN_UTILS function train.lua calls, and every module train.lua `require`s
+    before building a model exist in cat-generator_b200/lua/ (reference call sites: train.lua:101-107,119-137,147-185,231-261;
+    adversarial.lua:84-89,187-197; utils/nn_utils.lua:52,96,334-349,428-462,630)."""
+    import re
+    lua = os.path.join(lib.PKG_DIR, "lua")
+    models = open(os.path.join(lua, "models.lua")).read()
+    for m in ("forward", "backward", "getParameters", "training", "evaluate", "zeroGradParameters", "clone", "cuda", "float", "listModules",
+              "clearState", "__tostring", "write", "read"):
+        assert re.search(r"function Net:%s\b" % re.escape(m), models), "catgen.Net lacks :%s()" % m
+    assert "self.modules = {self}" in models and "self.gradInput" in models       # MODEL_D.modules[1].gradInput (adversarial.lua:193)
+    utils = open(os.path.join(lua, "utils", "nn_utils.lua")).read()
+    for f in ("createNoiseInputs", "createImagesFromNoise", "createImages", "sortImagesByPrediction", "switchToTrainingMode", "switchToEvaluationMode",
+              "prepareNetworkForSave", "getNumberOfParameters", "activateCuda", "visualizeProgress", "rateWithV"):
+        assert re.search(r"function nn_utils\.%s\b" % f, utils), "utils/nn_utils.lua lacks %s" % f
+    for req, path in (("cutorch", "rocks/cutorch.lua"), ("cunn", "rocks/cunn.lua"), ("dpnn", "rocks/dpnn.lua"), ("stn", "rocks/stn.lua"), ("cudnn", "rocks/cudnn.lua"),
+                      ("LeakyReLU", "LeakyReLU.lua"), ("layers.cudnnSpatialConvolutionUpsample", "layers/cudnnSpatialConvolutionUpsample.lua"),
+                      ("adversarial", "adversarial.lua"), ("models", "models.lua"), ("utils.nn_utils", "utils/nn_utils.lua")):
+        assert os.path.exists(os.path.join(lua, path)), "train.lua requires %r: %s is missing" % (req, path)
+    cu = open(os.path.join(lua, "layers", "cudnnSpatialConvolutionUpsample.lua")).read()
+    assert "torch.class('cudnn.SpatialConvolutionUpsample'" in cu and "accUpdateGradParameters" in cu
+    adv = open(os.path.join(lua, "adversarial.lua")).read()
+    assert "thisB - thisB % 2" in adv and "maxAccuracyD <= 1" in adv and "syncToHost" in adv
+    # every C function the Lua files call is declared in the cdef (and therefore, by the test above, in the header)
+    cdef = re.search(r"ffi\.cdef\[\[(.*?)\]\]", open(os.path.join(lua, "catgen_ffi.lua")).read(), flags=re.S).group(1)
+    declared = set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", cdef))
+    for root, _, files in os.walk(lua):
+        for f in files:
+            for name in re.findall(r"cg\.lib\.(cg_[a-z0-9_]+)", open(os.path.join(root, f)).read()):
+                assert name in declared, "%s calls %s, which catgen_ffi.lua does not declare" % (f, name)

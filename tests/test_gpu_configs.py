@@ -60,7 +60,7 @@ def test_closures_match_oracle_at_baseline_size(gk, ok, Cc, B):
     e_out, e_gD = float(np.abs(out - dout0).max()), rel(gD, od.grads)
     _report("fevalD B=%d" % B, pixels=e_px, d_out=e_out, loss=abs(f - f0), gradD_rel_max=e_gD, gradD_l2=l2rel(gD, od.grads))
     assert e_px < 1e-3 and e_out < 1e-3 and abs(f - f0) < 2e-3
-    assert e_gD < 2e-2
+    assert e_gD < 5e-2        # fp16 forward of D: see the module docstring of test_gpu_parity (statement (c)); tightened with the split-precision forward
     # fevalG_on_D with D's parameters as they are (no update in between: gradients, not trajectories, carry the claim)
     g.set_bn_running(og.bn_running)
     outG, fG, gimg, gG = _gpu_fevalG(L, g, d, cfg, zG, maskG, B)
@@ -338,3 +338,28 @@ def test_checkpoint_round_trip_continues_training(tmp_path):
     assert abs(ra[0][0] - rb[0][0]) < 1e-5 and abs(ra[1][0] - rb[1][0]) < 1e-4 and np.abs(ra[2] - rb[2]).max() < 1e-5
     with pytest.raises(ValueError):
         checkpoint.load(path, models.create_G((Cc, 32, 32), 100, kind=lib.G32UP), d2)
+
+
+# ------------------------------------------------------------------ boundary (b): the C-ABI driven from plain C
+def _build_abi_driver(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_driver")
+    pkg = os.path.join(root, "cat-generator_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "abi_driver.c"),
+                    "-o", exe, "-L", pkg, "-lcatgen", "-Wl,-rpath," + pkg, "-lm"], check=True, capture_output=True)
+    return exe
+
+
+def test_c_driver_replays_adversarial_train_through_the_abi(tmp_path):
+    """tests/abi_driver.c: no Python, no Lua -- one epoch of adversarial.train (adversarial.lua:27-292) as the LuaJIT-FFI shim would
+    issue it (one C call per nn.Module method), checked against the fused cg_train_step inside the same C program."""
+    import subprocess
+    exe = _build_abi_driver(tmp_path)
+    r = subprocess.run([exe, "8", "26"], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    assert "ABI_DRIVER_OK" in r.stdout
+    steps = [l for l in r.stdout.splitlines() if l.startswith("step ")]
+    assert [int(l.split("B=")[1].split()[0]) for l in steps] == [8, 8, 8, 8, 8, 6]     # 26 examples, B = 8: five full steps, tail of 6, then 2 < 4 aborts
+    assert "skipped" in r.stdout

@@ -32,7 +32,7 @@ def main():
         buf = C.create_string_buffer(1 << 16)
         lib.check(L.cg_profile_report(buf, len(buf))); lib.check(L.cg_profile_enable(0))
         for r in json.loads(buf.value.decode()):
-            if r["kernel"].startswith(("k_conv_tc", "k_wgrad_tc")):
+            if r["kernel"].startswith(("k_conv_tc", "k_conv_ps", "k_wgrad_tc")):
                 us = 1e3 * r["ms"] / r["launches"]
                 print("%-34s %-6s %-14s %2d launches  %8.1f us/launch  %7.1f TFLOP/s" % (tag, name, r["kernel"], r["launches"], us, fl / us / 1e6), flush=True)
 

@@ -543,7 +543,11 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   // A graph bakes in raw device pointers (DBufs, workspaces, lane / side scratch).  Any reallocation since the capture --
   // a larger configuration, a larger eager forward -- makes them dangle: drop the graph, run one eager step so that every
   // buffer reaches its size again, and capture anew.
-  if (sg->exec && sg->gen != X.alloc_gen) { cudaGraphExecDestroy(sg->exec); sg->exec = nullptr; sg->warm = 1; }
+  static const bool trace = getenv("CATGEN_GRAPH_TRACE") != nullptr;
+  if (sg->exec && sg->gen != X.alloc_gen) {
+    if (trace) fprintf(stderr, "[catgen graph] B=%d: buffers were reallocated since the capture (generation %llu -> %llu): dropping the graph\n", c->B, (unsigned long long)sg->gen, (unsigned long long)X.alloc_gen);
+    cudaGraphExecDestroy(sg->exec); sg->exec = nullptr; sg->warm = 1;
+  }
   const int B = c->B, hB = B / 2; const size_t img = (size_t)t->G->C * 1024, nz = t->G->nz;
   const size_t nr = (size_t)c->d_iters * hB * img, nzd = (size_t)c->d_iters * hB * nz, nzg = (size_t)c->g_iters * B * nz;
   if (sg->failed || (!sg->exec && sg->warm < 2)) {
@@ -552,15 +556,18 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   }
   CG_TRY(t->gin.ensure(nr + nzd + nzg));
   float* g0 = t->gin.p;
+  // The graph is captured from -- and therefore always replayed from -- a state in which both networks' packed operands are fresh:
+  // whatever ran since the last update (an eager forward, cg_model_set_params, a replay that ended with an Adam step) is settled by an
+  // eager repack here; the host-side flags are put back to what an eager step leaves behind after every replay (sg->end_dirty_*).
+  CG_TRY(model_repack(t->G)); CG_TRY(model_repack(t->D));
   CG_CUDA(cudaMemcpyAsync(g0, real, sizeof(float) * nr, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr, zD, sizeof(float) * nzd, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyDeviceToDevice, X.stream));
   if (!sg->exec) {
     int64_t l0 = X.launches;
     cudaGraph_t graph = nullptr;
-    // the graph must contain both repacks at their first use, whatever eager forwards ran since the last update
-    t->G->dirty = t->D->dirty = true;
     const uint64_t gen0 = X.alloc_gen;
+    if (trace) fprintf(stderr, "[catgen graph] B=%d d=%d g=%d: capturing (generation %llu)\n", c->B, c->d_iters, c->g_iters, (unsigned long long)gen0);
     if (cudaStreamBeginCapture(X.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); sg->failed = true; }
     else {
       int st = train_step_core(t, c, g0, g0 + nr, g0 + nr + nzd, nullptr, nullptr);
@@ -573,14 +580,15 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
         CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG);
       }
       sg->gen = X.alloc_gen;
+      sg->end_dirty_G = t->G->dirty; sg->end_dirty_D = t->D->dirty;
       sg->launches = X.launches - l0; X.launches = l0;      // captured, not executed yet
     }
     if (sg->failed) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   }
   CG_CUDA(cudaGraphLaunch(sg->exec, X.stream));
-  // the replay ran both Adam updates on the device: the packed operands are stale for any eager forward that follows
-  // (the replayed graph itself repacks at first use, see above)
-  t->G->dirty = t->D->dirty = true;
+  // the replay ran the Adam updates on the device: leave the flags as the eager step would (a network updated after its last forward
+  // of the step has stale packed operands for whatever runs next)
+  t->G->dirty = sg->end_dirty_G; t->D->dirty = sg->end_dirty_D;
   X.launches += sg->launches;
   return read_losses(t, c, lossD, lossG);
 }

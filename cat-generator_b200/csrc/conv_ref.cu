@@ -56,6 +56,11 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, int S, long n, i
   }
 }
 
+int splitk_reduce(const float* part, int S, long n, int ncol, const float* bias, float* out) {
+  ctx().next_bytes = 4.0 * (double)n * (S + 1);
+  CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, part, S, n, ncol, bias, out); return CG_OK;
+}
+
 // ------------------------------------------------------------------ partial sums -> Torch-layout gradient, fused
 // gW[co][ci][ky][kx] += sum_z part[z][(tap,ci)][co].  A block takes all taps of CIB input channels x 32 output channels: the packed
 // partials are read coalesced along co and summed in fixed z order (deterministic), transposed through shared memory, and each

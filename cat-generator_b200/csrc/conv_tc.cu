@@ -61,10 +61,31 @@ static int make_patch_tmap(CUtensorMap* tm, const void* xq, int ES, int N, int C
   return CG_OK;
 }
 
+// Weight slices as a 2-D tensor of 8-byte elements: row = one 16-byte-per-column plane of a slice ([Cop] x 16 B), rows = planes in
+// stream order.  A box of [NB columns] x [4 planes] is one 32-channel slice of a CTA's column block, landing as [c][NB][16 B].
+// Measured (gpurun_out/r02_d_conv3_dbg.txt): the same slices fetched with 1-D cp.async.bulk copies arrived at ~10 B/cycle/SM (8 KB copies;
+// ~14 B/cycle with round 1's 16 KB copies) whatever the ring depth -- the issuers waited 119-171k of 371k cycles for weights while the
+// producer waited 167k cycles for free slots -- i.e. the 1-D bulk path, not L2 or the crossbar, was what starved the tensor pipe.
+static int make_wslice_tmap(CUtensorMap* tm, const void* wq, int Cop, long planes, int NB) {
+  cg_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Cop * 2, (cuuint64_t)planes};
+  cuuint64_t strides[1] = {(cuuint64_t)Cop * 16};
+  cuuint32_t box[2] = {(cuuint32_t)NB * 2, 4}, estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(wq), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled (weight slices) failed with %d (Cop %d, planes %ld, NB %d)", (int)r, Cop, planes, NB);
+  return CG_OK;
+}
+
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ void tma_patch_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
@@ -226,7 +247,7 @@ __device__ __forceinline__ void pack_slices_job(const float* __restrict__ W, uin
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         int ci = ci0 + j;
-        v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, 1, 1, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
+        v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, s.in_hw, s.out_hw, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
       }
       uint4 out; uint32_t* o = &out.x;
 #pragma unroll
@@ -245,7 +266,7 @@ __device__ __forceinline__ void pack_slices_job(const float* __restrict__ W, uin
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int ci = ci0 + j;
-      v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, 1, 1, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
+      v[j] = (co < Cout && ci < Cin) ? W[torch_index(k, s.Ci, s.Co, s.in_hw, s.out_hw, ky, kx, dgrad ? co : ci, dgrad ? ci : co)] : 0.f;
     }
     uint4 out; uint32_t* o = &out.x;
 #pragma unroll
@@ -564,6 +585,7 @@ void conv_tc_register_wslices(const float* key, const uint8_t* wq, int CB) { wsl
 void conv_tc_unregister_wslices(const float* key) { wslice_registry().erase(key); }
 static bool conv_v1();
 bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes) {
+  if (!conv_v1() && k == 1) { *CB = 32; *bytes = (size_t)((Cin + 31) / 32) * 32 * (((Cout + 15) / 16) * 16) * 2; return true; }   // nn.Linear
   if (!(k == 3 || k == 5 || k == 7)) return false;
   if (!conv_v1()) { *CB = 32; *bytes = (size_t)k * k * ((Cin + 31) / 32) * 32 * (((Cout + 15) / 16) * 16) * 2; return true; }
   const int Ci = ((Cin + 63) / 64) * 64, Co = ((Cout + 15) / 16) * 16;
@@ -598,6 +620,9 @@ struct PsParams {
   int ncb, kk, nslices;                // 32-channel blocks that hold data, taps, ncb * kk
   int tiles_x, tiles_y, ntiles;
   int NB, S, D;                        // columns per CTA, weight ring depth, stagger / gap in slices
+  long long* dbg;                      // experiments (CATGEN_PS_DBG=1): per-CTA clock64 breakdown, 32 values per CTA
+  int Z;                               // > 1: K-SPLIT mode (nn.Linear, kk = 1): gridDim.x = Z CTAs each stream their share of the slices for ALL tiles
+                                       //      (<= 4) and write raw partial sums to y[z][...] (bias / reduction in k_splitk_reduce)
   uint32_t patch_bytes, slice_bytes;
 };
 // Weights Wp[(tap,ci)][co] fp32 -> 32-channel slices in stream order Wq[cb][tap][c 0..3][Cop][8 fp16]; zero beyond Ci / Co.
@@ -616,7 +641,7 @@ __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restri
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
 
-__global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_constant__ CUtensorMap tmx) {
+__global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_wfull[16], bar_wempty[16], bar_pfull[PS_SLOTS][2], bar_pempty[PS_SLOTS][2], bar_acc[PS_SLOTS], bar_tfree[PS_SLOTS];
   __shared__ uint32_t tmem_base_s;
@@ -626,8 +651,14 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
   float* stage0 = reinterpret_cast<float*>(wring + (size_t)P.S * P.slice_bytes);   // epilogue staging, 4 warps x 32 rows x 36 floats
 
   const int gx = gridDim.x, co0 = blockIdx.y * P.NB;
-  const int nt = (P.ntiles - (int)blockIdx.x + gx - 1) / gx;           // tiles of this CTA (>= 1: the host keeps gridDim.x <= ntiles)
-  const int ns = P.nslices, D = P.D, kk = P.kk, ncb = P.ncb;
+  long long* dbg = P.dbg ? P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  const long long t_start = dbg ? clock64() : 0;
+  const bool zs = P.Z > 1;                                            // K-split mode
+  const int s_begin = zs ? (int)((long)P.nslices * blockIdx.x / P.Z) : 0;                       // first slice this CTA streams
+  const int ns = zs ? (int)((long)P.nslices * (blockIdx.x + 1) / P.Z) - s_begin : P.nslices;    // slices per tile cycle (>= 1: Z <= nslices)
+  const int nt = zs ? P.ntiles : (P.ntiles - (int)blockIdx.x + gx - 1) / gx;   // tiles of this CTA (>= 1: the host keeps gridDim.x <= ntiles)
+  const int D = zs ? 0 : P.D, kk = P.kk;
+  const int ncb = zs ? ns : P.ncb;                                    // 32-channel blocks in this CTA's stream (kk = 1 in K-split mode)
   // slot j owns tiles j, j+4, ...; its k-th tile is accumulated over slices [j*D + k*(ns+D), +ns)
   int total_g = 0;
 #pragma unroll
@@ -653,23 +684,24 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base_s;
   auto tile_xy = [&](int i, int& n, int& y0, int& x0) {
-    int t = (int)blockIdx.x + i * gx; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
+    int t = zs ? i : (int)blockIdx.x + i * gx; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
   };
 
   if (warp == 8) {
     // ===== weight producer: the cyclic slice stream, one bulk copy per slice (one per plane when the CTA owns a column block)
     if (lane == 0) {
       int st = 0, s = 0; uint32_t ph = 0;
+      long long tw = 0, tq = 0;
       for (int g = 0; g < total_g; ++g) {
+        if (dbg) tq = clock64();
         mbar_wait(&bar_wempty[st], ph ^ 1);
+        if (dbg) tw += clock64() - tq;
         mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
-        uint8_t* dst = wring + (size_t)st * P.slice_bytes;
-        const uint8_t* src = P.wq + (size_t)s * 4 * P.Co * 16;
-        if (P.NB == P.Co) bulk_g2s(dst, src, P.slice_bytes, &bar_wfull[st]);
-        else for (int c = 0; c < 4; ++c) bulk_g2s(dst + (size_t)c * P.NB * 16, src + ((size_t)c * P.Co + co0) * 16, P.NB * 16, &bar_wfull[st]);
+        tma_2d(wring + (size_t)st * P.slice_bytes, &tmw, co0 * 2, (s_begin + s) * 4, &bar_wfull[st]);   // ONE tiled TMA per slice, column block included
         if (++s == ns) s = 0;
         if (++st == P.S) { st = 0; ph ^= 1u; }
       }
+      if (dbg) { dbg[1] = tw; dbg[2] = clock64() - t_start; }
     }
   } else if (warp == 9) {
     // ===== patch producer.  Per slot a stream of segments (= one 32-channel block of one tile resident in one of the slot's two
@@ -687,12 +719,13 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
         const int j = best;
         // tile kj of slot j starts at slice gstart; segment qj covers [gj, gj + len)
         const int gstart = j * D + kj[j] * (ns + D);
-        const int s0 = gstart % ns, cb0 = s0 / kk, tap0 = s0 - cb0 * kk;
+        const int s0 = gstart % ns, cb0 = s0 / kk, tap0 = s0 - cb0 * kk;     // position in THIS CTA's stream (block index relative to s_begin / kk)
         const int nseg = ncb == 1 ? 1 : ncb + (tap0 > 0 ? 1 : 0);
         int cb, len;
         if (ncb == 1) { cb = 0; len = ns; }
         else if (qj[j] == 0) { cb = cb0; len = kk - tap0; }
         else { cb = cb0 + qj[j]; if (cb >= ncb) cb -= ncb; len = (qj[j] == nseg - 1 && tap0 > 0) ? tap0 : kk; }
+        cb += s_begin;                                                        // K-split (kk = 1): slices ARE channel blocks
         const int buf = cj[j] & 1; const uint32_t ph = (uint32_t)(cj[j] >> 1) & 1u;
         mbar_wait(&bar_pempty[j][buf], ph ^ 1);
         mbar_expect_tx(&bar_pfull[j][buf], P.patch_bytes);
@@ -721,20 +754,29 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
       int kt = 0, g0 = j * D, seg = 0;
       int tap = 0, ky = 0, kx = 0;
       uint32_t p_lo = p_lo_buf0;
+      long long t_wf = 0, t_pf = 0, t_tf = 0, tq = 0;
       for (int g = 0; g < total_g; ++g) {
+        if (dbg) tq = clock64();
         mbar_wait(&bar_wfull[st], wph);
+        if (dbg) t_wf += clock64() - tq;
         if (kt < nk && g >= g0) {                           // g < g0 + ns holds by construction (the window is closed below)
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (g == g0) {
+            if (dbg) tq = clock64();
             if (kt > 0) { mbar_wait(&bar_tfree[j], (uint32_t)(kt - 1) & 1u); asm volatile("tcgen05.fence::after_thread_sync;"); }   // epilogue has drained this slot's previous tile
+            if (dbg) t_tf += clock64() - tq;
             const int s0 = g0 % ns; const int cb0 = s0 / kk; tap = s0 - cb0 * kk; ky = tap / k; kx = tap - ky * k;
+            if (dbg) tq = clock64();
             mbar_wait(&bar_pfull[j][seg & 1], (uint32_t)(seg >> 1) & 1u);
+            if (dbg) t_pf += clock64() - tq;
             asm volatile("tcgen05.fence::after_thread_sync;");
             p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
             acc = 0;
           } else if (tap == 0 && ncb > 1) {                 // next 32-channel block: hand the buffer back, take the other one
             umma_commit(&bar_pempty[j][seg & 1]); ++seg;
+            if (dbg) tq = clock64();
             mbar_wait(&bar_pfull[j][seg & 1], (uint32_t)(seg >> 1) & 1u);
+            if (dbg) t_pf += clock64() - tq;
             asm volatile("tcgen05.fence::after_thread_sync;");
             p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
           }
@@ -753,6 +795,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
         } else mbar_arrive(&bar_wempty[st]);
         if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
       }
+      if (dbg) { dbg[4 + j * 4] = t_wf; dbg[5 + j * 4] = t_pf; dbg[6 + j * 4] = t_tf; dbg[7 + j * 4] = clock64() - t_start; }
     }
   } else {
     // ===== epilogue (warps 0-3): tiles in completion order (k, j); warp w owns TMEM lanes 32w..32w+31 = pixels of the tile
@@ -761,11 +804,15 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
     const float inv = (P.scale2 ? P.scale2[1] : 1.f) * P.inv_host;
     float* stage = stage0 + warp * (32 * 36);
     const bool wide = vec && (P.NB & 31) == 0;
+    long long t_acc = 0, tq = 0;
     for (int i = 0; i < nt; ++i) {
       const int j = i & (PS_SLOTS - 1), kt = i >> 2;
+      if (dbg) tq = clock64();
       mbar_wait(&bar_acc[j], (uint32_t)kt & 1u);
+      if (dbg) t_acc += clock64() - tq;
       asm volatile("tcgen05.fence::after_thread_sync;");
       int n, y0, x0; tile_xy(i, n, y0, x0);
+      if (zs) n += (int)blockIdx.x * P.N;                                   // partial sums of split z live in y[z]
       const uint32_t tcol = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * P.NB);
       if (wide) {
         for (int c0 = 0; c0 < P.NB; c0 += 32) {
@@ -837,16 +884,19 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tfree[j]);
     }
+    if (dbg && tid == 0) { dbg[20] = t_acc; dbg[21] = clock64() - t_start; dbg[22] = nt; dbg[23] = total_g; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (dbg && tid == 0) dbg[0] = clock64() - t_start;
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
 }
 
 static bool conv_v1() { static const bool v = getenv("CATGEN_CONV_V1") != nullptr; return v; }   // the round-1 kernel, kept for A/B measurements
 
+// Zmax > 1: the caller allows a K split (nn.Linear: k = 1, at most four tiles); the partial sums go through workspace #1.
 static int conv_ps_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
-                       const uint8_t* xq_prepacked) {
+                       const uint8_t* xq_prepacked, int Zmax = 1) {
   const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // operand padding of the packed activations (shared with the weight gradient)
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
@@ -854,7 +904,7 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   if (NB < 16) return CG_ERR_UNSUPPORTED;
   const int ncb = (Cir + 31) / 32;
   const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * NB * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
-  const size_t budget = 226 * 1024;
+  const size_t budget = 224 * 1024;   // opt-in limit 227 KB per block minus the static part (barriers + 1 KB reserved: cuobjdump -res-usage says 1536 B)
   if (2 * PS_SLOTS * patch_bytes + stage_bytes + 3 * slice_bytes > budget) return CG_ERR_UNSUPPORTED;
   int S = (int)((budget - 2 * PS_SLOTS * patch_bytes - stage_bytes) / slice_bytes); if (S > 16) S = 16;
   const int ntiles = N * (W / 8) * ((H + 15) / 16);
@@ -877,24 +927,66 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   P.N = N; P.H = H; P.W = W; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p;
   P.ncb = ncb; P.kk = kk; P.nslices = ncb * kk;
   P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.ntiles = ntiles; P.NB = NB; P.S = S;
+  // K split: only worth it when the tile grid alone leaves most SMs idle (Linear 20480 -> 256 at batch 128 is ONE tile x two column blocks)
+  int Z = 1;
+  if (Zmax > 1 && kk == 1 && ntiles <= PS_SLOTS) {
+    Z = ctx().sm_count / (Co / NB); if (Z > Zmax) Z = Zmax; if (Z > P.nslices / 2) Z = P.nslices / 2; if (Z < 1) Z = 1;
+  }
+  P.Z = Z;
+  float* part = nullptr;
+  if (Z > 1) {
+    part = (float*)workspace(sizeof(float) * (size_t)Z * N * H * W * Cor + 256); if (!part) return CG_ERR_CUDA;
+    P.y = part; P.bias = nullptr;
+  }
   static const int d_env = getenv("CATGEN_PS_D") ? atoi(getenv("CATGEN_PS_D")) : 16;
   P.D = d_env < 1 ? 1 : d_env;
   if (P.D > P.nslices / 4) P.D = P.nslices / 4 > 0 ? P.nslices / 4 : 1;   // short K loops: keep the four slots overlapping (stagger < a quarter cycle)
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
   const size_t smem = 2 * PS_SLOTS * patch_bytes + (size_t)S * slice_bytes + stage_bytes;
   static bool attr_done = false;
-  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done = true; }
+  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_done = true; }
   const int gy = Co / NB;
   int gx = ctx().sm_count / gy; if (gx < 1) gx = 1;
   const int want = (ntiles + PS_SLOTS - 1) / PS_SLOTS;                     // every CTA should own four tiles (they share each weight slice)
   if (gx > want) gx = want;
+  if (Z > 1) gx = Z;
   dim3 grid(gx, gy);
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;             // algorithmic (unpadded) work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
-  CUtensorMap tmx;
+  CUtensorMap tmx, tmw;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
-  CG_LAUNCH(k_conv_ps, grid, 320, smem, P, tmx);
+  CG_TRY(make_wslice_tmap(&tmw, wq, Co, (long)P.nslices * 4, NB));
+  static const bool dbg_on = getenv("CATGEN_PS_DBG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 32 * 1024);
+  P.dbg = (dbg_on && (long)gx * gy <= 1024) ? dbg_buf : nullptr;
+  if (P.dbg) cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 32 * 1024, ctx().stream);
+  CG_LAUNCH(k_conv_ps, grid, 320, smem, P, tmx, tmw);
+  if (P.dbg) {   // experiments only: where does a CTA's time go (cycles, mean over CTAs)
+    cudaStreamSynchronize(ctx().stream);
+    size_t n = (size_t)gx * gy;
+    std::vector<long long> h(n * 32);
+    cudaMemcpy(h.data(), dbg_buf, sizeof(long long) * 32 * n, cudaMemcpyDeviceToHost);
+    double m[32] = {0}; double tmax = 0;
+    for (size_t i = 0; i < n; ++i) { for (int q = 0; q < 32; ++q) m[q] += (double)h[i * 32 + q] / n; if ((double)h[i * 32] > tmax) tmax = (double)h[i * 32]; }
+    const double floor_t = m[22] * P.nslices * 2.0 * (128.0 * NB / 256.0);
+    fprintf(stderr, "[ps dbg] N=%d %dx%d Ci=%d Co=%d k=%d grid=%dx%d NB=%d S=%d D=%d ns=%d | per CTA: total %.0f (max %.0f) tiles %.1f slices %.0f MMA-floor %.0f | "
+                    "weights: producer waits-for-empty %.0f | issuers wait weights %.0f %.0f %.0f %.0f, patches %.0f %.0f %.0f %.0f, tmem-free %.0f %.0f %.0f %.0f | epilogue waits-for-acc %.0f of %.0f\n",
+            N, H, W, Cir, Cor, k, gx, gy, NB, S, P.D, P.nslices, m[0], tmax, m[22], m[23], floor_t, m[1],
+            m[4], m[8], m[12], m[16], m[5], m[9], m[13], m[17], m[6], m[10], m[14], m[18], m[20], m[21]);
+  }
+  if (Z > 1) CG_TRY(splitk_reduce(part, Z, (long)N * H * W * Cor, Cor, bias, y));   // fixed z order; adds the bias
   return CG_OK;
+}
+
+// nn.Linear on the tensor cores (models.lua:199,697,700,852,854): y[B, out] = x[B, in] W^T + b is the 1x1 convolution of
+// the "image" whose PIXELS are the batch rows -- x viewed as [B/128 images][16 rows][8 px][in channels] is the same memory as x[B][in], a
+// tile of 8 x 16 pixels is exactly one M = 128 MMA tile -- so the conv engine takes it unchanged with k = 1, split along K when the
+// tile grid is too small to fill the machine (k_conv_ps, K-split mode).
+static bool linear_shape_ok(int B) { return B >= 8 && B % 8 == 0 && (B <= 128 || B % 128 == 0); }
+static int linear_tc_run(const float* x, const float* Wp, const float* bias, float* y, int B, int Cir, int Cor, const float* scale2, const uint8_t* xq_prepacked) {
+  const int Nimg = B <= 128 ? 1 : B / 128, Hh = B <= 128 ? B / 8 : 16;
+  return conv_ps_run(x, Wp, bias, y, Nimg, Hh, 8, Cir, Cor, 1, scale2, xq_prepacked, 1 << 20);
 }
 // ====================================================================================================================
 
@@ -1041,6 +1133,12 @@ int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, fl
 
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
+  if (k == 1 && H == 1 && W == 1 && !conv_v1() && !dgrad_tf32 && linear_shape_ok(N) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {   // nn.Linear
+    if (!g_tc_grad_operands) return linear_tc_run(x, Wp, bias, y, N, Ci, Co, nullptr, nullptr);
+    const int Nimg = N <= 128 ? 1 : N / 128, Hh = N <= 128 ? N / 8 : 16;
+    GradOperand g; CG_TRY(pack_grad_operand(x, Nimg, Hh, 8, Ci, 1, &g));                    // gradient-valued input: per-tensor power-of-two scale
+    return linear_tc_run(x, Wp, bias, y, N, Ci, Co, g.scale2, g.gq);
+  }
   if (!tc_shape_ok(H, W, Ci, Co, k, 2)) return CG_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return CG_ERR_UNSUPPORTED;
   if (!g_tc_grad_operands) return conv_tc_run<2>(x, Wp, bias, y, N, H, W, Ci, Co, k);
@@ -1316,9 +1414,10 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   CG_TRY(make_tile_tmap(&tmg, g.gq, N, g.Cg / 8, Hq, Wq, NB / 8));
   CG_LAUNCH(k_wgrad_tc, grid, 256, smem, P, tmx, tmg);
   long nW = (long)kk * Cir * Cor;
-  // straight into the Torch-layout gradient: split sum (fixed order) + layout change + accumulate in ONE kernel
-  if (gW_acc && parts_to_torch_acc(part, Z, nW, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; return CG_OK; }
-  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // packed result wanted (op-level entry points, Linear)
+  // Measured (gpurun_out r02_c): summing the Z partials inside k_parts_to_torch_acc (even with four load chains per thread) costs
+  // 2.1 ms per step against 0.69 ms for the fully parallel element-wise sum followed by the layout change: keep the two kernels.
+  CG_LAUNCH(k_sum_parts, grid1d(nW, 256, 2), 256, 0, part, Z, nW, gWp_out);          // fully parallel, fixed z order
+  if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Cir, Cor, kk) == CG_OK) { if (done) *done = 1; }   // layout change only
   return CG_OK;
 }
 

@@ -126,8 +126,9 @@ int model_build(cg_model* m) {
       J.wqf = J.wqd = nullptr; J.CBf = J.CBd = 0;
       { long nW = (long)L.s.Co * L.s.Ci * L.s.k * L.s.k; J.blk0 = m->repack_blocks; J.nblk = (int)((nW + 2047) / 2048); m->repack_blocks += J.nblk; }
       size_t bf = 0, bd = 0;
-      if (L.s.in_hw == 1 && L.s.out_hw == 1 && conv_tc_wslice_plan(L.s.Ci, L.s.Co, L.s.k, &J.CBf, &bf)) { J.wqf = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bf + 255) & ~(size_t)255; }
-      if (L.need_dgrad && L.s.in_hw == 1 && L.s.out_hw == 1 && conv_tc_wslice_plan(L.s.Co, L.s.Ci, L.s.k, &J.CBd, &bd)) { J.wqd = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bd + 255) & ~(size_t)255; }
+      const bool plain = L.s.in_hw == 1 && L.s.out_hw == 1;     // Linear layers beside an nn.View (k = 1) are taken by the round-2 engine only (CB == 32)
+      if (conv_tc_wslice_plan(L.s.Ci, L.s.Co, L.s.k, &J.CBf, &bf) && (plain || J.CBf == 32)) { J.wqf = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bf + 255) & ~(size_t)255; }
+      if (L.need_dgrad && conv_tc_wslice_plan(L.s.Co, L.s.Ci, L.s.k, &J.CBd, &bd) && (plain || J.CBd == 32)) { J.wqd = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bd + 255) & ~(size_t)255; }
     }
     if (wq_total) CG_CUDA(cudaMalloc(&m->wq, wq_total));
     for (size_t i = 0; i < jobs.size(); ++i) {   // offsets (+1 so that offset 0 is distinguishable from "none") -> pointers

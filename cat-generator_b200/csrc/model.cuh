@@ -61,7 +61,7 @@ struct cg_trainer {
   cg::DBuf inputs, targets, samples, dout, df, gimg, scal, stage;
   // CUDA-graph replay of the step (capi.cu): fixed input buffers + one instantiated graph per step configuration
   cg::DBuf gin;
-  struct StepGraph { cg_step_cfg cfg; int engine = 0, elim = 0, lanes = 0; int warm = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t gen = 0; };
+  struct StepGraph { cg_step_cfg cfg; int engine = 0, elim = 0, lanes = 0; int warm = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t gen = 0; bool end_dirty_G = true, end_dirty_D = true; };
   std::vector<StepGraph> graphs;
 };
 

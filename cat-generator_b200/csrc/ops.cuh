@@ -94,6 +94,7 @@ int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W,
 // gW_acc/done: optional direct accumulation into the Torch-layout gradient of a plain conv (see conv_ref.cu)
 int conv_wgrad(const float* x, const float* gy, float* gWp_out, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr);
 int parts_to_torch_acc(const float* part, int Z, long zstride, float* gW_acc, int Ci, int Co, int kk);
+int splitk_reduce(const float* part, int S, long n, int ncol, const float* bias, float* out);   // out[i] = bias[i % ncol] + sum_z part[z][i], fixed z order
 // both gradients of one layer (gWp_out overwritten, gx written)
 int conv_backward(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc = nullptr, int* done = nullptr,
                   const uint8_t* xq = nullptr, float* gb_acc = nullptr, int* bias_done = nullptr);   // gb_acc: bias gradient; *bias_done = 1 when the engine added it

@@ -137,22 +137,28 @@ def test_conv_upsample_module():
     assert b"odd" in L.cg_last_error()
 
 
-@pytest.mark.parametrize("N,inn,out", [(8, 100, 8192), (4, 20480, 256), (5, 256, 1), (3, 64, 4), (1, 7, 3)])
-def test_linear(N, inn, out):
+@pytest.mark.parametrize("N,inn,out", [(8, 100, 8192), (4, 20480, 256), (5, 256, 1), (3, 64, 4), (1, 7, 3),
+                                       (128, 20480, 256), (64, 100, 8192), (256, 256, 1), (128, 1024, 64), (128, 64, 4)],
+                         ids=lambda v: str(v))
+def test_linear(N, inn, out, engine):
+    """nn.Linear (models.lua:199,697,700,852,854).  On the tensor-core engine batches that are a multiple of 8 (<= 128) or of 128 run
+    forward and input gradient as a 1x1 convolution over the batch rows on tcgen05, split along K when the tile grid is small
+    (csrc/conv_tc.cu linear_tc_run); fp16 operands, fp32 accumulate: 3e-3 of max.  The weight gradient stays on the fp32 kernel."""
     L, O = lib.load(), po.lib()
     rng = np.random.default_rng(N * 1000 + out)
     x = rng.uniform(-1, 1, (N, inn)).astype(np.float32)
     W = (rng.uniform(-1, 1, (out, inn)) / np.sqrt(inn)).astype(np.float32)
     b = rng.uniform(-0.1, 0.1, out).astype(np.float32)
     gy = rng.standard_normal((N, out)).astype(np.float32)
+    tol = OP_TOL if (engine == 0 or N % 8) else 3e-3
     y, y0 = np.empty((N, out), np.float32), np.empty((N, out), np.float32)
     lib.check(L.cg_linear_fwd(P(x), P(W), P(b), P(y), N, inn, out)); O.og_linear_fwd(po.P(x), po.P(W), po.P(b), po.P(y0), N, inn, out)
-    assert rel(y, y0) < OP_TOL
+    assert rel(y, y0) < tol
     gx, gW, gb = np.empty_like(x), np.ones_like(W), np.ones_like(b)
     gx0, gW0, gb0 = np.empty_like(x), np.ones_like(W), np.ones_like(b)
     lib.check(L.cg_linear_bwd(P(x), P(gy), P(W), P(gx), P(gW), P(gb), N, inn, out))
     O.og_linear_bwd(po.P(x), po.P(gy), po.P(W), po.P(gx0), po.P(gW0), po.P(gb0), N, inn, out)
-    assert rel(gx, gx0) < OP_TOL and rel(gW, gW0) < OP_TOL and rel(gb, gb0) < OP_TOL
+    assert rel(gx, gx0) < tol and rel(gW, gW0) < OP_TOL and rel(gb, gb0) < OP_TOL
 
 
 @pytest.mark.parametrize("N,Cc,HW", [(8, 512, 64), (4, 128, 1024), (3, 5, 7), (2, 1, 4)])
@@ -660,7 +666,9 @@ def test_full_size_properties_c2():
     assert np.array_equal(px, px2), "G forward is deterministic (split-K partials are reduced in fixed order)"
     # batch statistics: permuting the batch permutes the output (BN couples samples only through symmetric sums)
     perm = rng.permutation(B)
-    assert np.abs(g.forward(z[perm]) - px[perm]).max() < 1e-4
+    # the persistent conv kernel starts each tile's K loop at a slice that depends on the tile's position in the launch, so permuting the
+    # batch changes the fp32 summation order: accumulation-order noise through four conv + BN layers (north_star tolerance: 1e-3)
+    assert np.abs(g.forward(z[perm]) - px[perm]).max() < 5e-4
     d.evaluate()
     o1 = d.forward(px); o2 = d.forward(px[perm])
     assert np.abs(o1[perm] - o2).max() < 1e-5, "D is per-sample in eval mode"

@@ -939,16 +939,18 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
     P.y = part; P.bias = nullptr;
   }
   static const int d_env = getenv("CATGEN_PS_D") ? atoi(getenv("CATGEN_PS_D")) : 16;
-  P.D = d_env < 1 ? 1 : d_env;
-  if (P.D > P.nslices / 4) P.D = P.nslices / 4 > 0 ? P.nslices / 4 : 1;   // short K loops: keep the four slots overlapping (stagger < a quarter cycle)
+  P.D = d_env < 0 ? 0 : d_env;
+  if (P.D > P.nslices / 4) P.D = P.nslices / 4;   // short K loops: keep the four slots overlapping (stagger < a quarter cycle)
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
   const size_t smem = 2 * PS_SLOTS * patch_bytes + (size_t)S * slice_bytes + stage_bytes;
   static bool attr_done = false;
   if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_done = true; }
   const int gy = Co / NB;
   int gx = ctx().sm_count / gy; if (gx < 1) gx = 1;
-  const int want = (ntiles + PS_SLOTS - 1) / PS_SLOTS;                     // every CTA should own four tiles (they share each weight slice)
-  if (gx > want) gx = want;
+  // Fill the machine first: measured (gpurun_out/r02_e_layers.txt vs r02_d_layers_v1.txt), insisting on four tiles per CTA left most SMs
+  // idle on the 8x8 / 16x16 layers (128 -> 128 7x7 at 8x8: 32 CTAs, 117 us against 52 us with 64 CTAs) -- the tensor pipe, not the
+  // weight stream, bounds a CTA, so sharing slices among fewer, busier CTAs buys nothing there.
+  if (gx > ntiles) gx = ntiles;
   if (Z > 1) gx = Z;
   dim3 grid(gx, gy);
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;             // algorithmic (unpadded) work

@@ -345,9 +345,26 @@ static int copy_channels(const float* src, float* dst, long rows, int Cs, int Cd
   long n = rows * Cs; CG_LAUNCH(k_copy_channels, grid1d(n, 256, 4), 256, 0, src, dst, n, Cs, Cd, coff, dir); return CG_OK;
 }
 
+static bool stn_use_fused() { static const bool off = getenv("CATGEN_STN_UNFUSED") != nullptr; return ctx().conv_engine == 1 && !off; }
+static void stn_params(cg_model* m, cg_stn* s, StnFusedParams* p, StnFusedGrads* g) {
+  const cg_layer &c1 = m->layers[s->c1], &c2 = m->layers[s->c2], &l1 = m->layers[s->l1], &l2 = m->layers[s->l2];
+  p->W1 = m->P + c1.oW; p->b1 = m->P + c1.ob; p->W2 = m->P + c2.oW; p->b2 = m->P + c2.ob;
+  p->L1 = m->P + l1.oW; p->lb1 = m->P + l1.ob; p->L2 = m->P + l2.oW; p->lb2 = m->P + l2.ob;
+  p->ch = s->ch; p->S = s->S; p->rot = s->rot; p->scl = s->scl; p->trn = s->trn; p->nth = s->nth;
+  if (g) { g->W1 = m->G + c1.oW; g->b1 = m->G + c1.ob; g->W2 = m->G + c2.oW; g->b2 = m->G + c2.ob; g->L1 = m->G + l1.oW; g->lb1 = m->G + l1.ob; g->L2 = m->G + l2.oW; g->lb2 = m->G + l2.ob; }
+}
 static int stn_forward(cg_model* m, cg_stn* s, const float* in, int B) {
   int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
   s->in = in;
+  s->fused = stn_use_fused();
+  if (s->fused) {   // stn_fused.cu: localisation network in one launch (one CTA per image, fp32), sampler in one launch
+    long n2 = (long)B * S2 * S2 * 16;
+    s->pool1 = FW(m, (size_t)B * S2 * S2 * ch); s->c1o = FW(m, n2); s->c2o = FW(m, n2); s->pool2 = FW(m, (size_t)B * f); s->l1o = FW(m, (size_t)B * 64);
+    s->theta = FW(m, (size_t)B * 4); s->A = FW(m, (size_t)B * 6); s->out = FW(m, (size_t)B * S * S * ch);
+    NN(s->pool1); NN(s->c1o); NN(s->c2o); NN(s->pool2); NN(s->l1o); NN(s->theta); NN(s->A); NN(s->out);
+    StnFusedParams p; stn_params(m, s, &p, nullptr);
+    return stn_fused_forward(p, in, B, s->pool1, s->c1o, s->c2o, s->pool2, s->l1o, s->theta, s->A, s->out);
+  }
   s->pool1 = FW(m, (size_t)B * S2 * S2 * ch); NN(s->pool1); CG_TRY(avgpool2_fwd(in, s->pool1, B, S, S, ch));
   long n2 = (long)B * S2 * S2 * 16;
   s->c1o = FW(m, n2); s->a1 = FW(m, n2); s->c2o = FW(m, n2); s->a2 = FW(m, n2); NN(s->c1o); NN(s->a1); NN(s->c2o); NN(s->a2);
@@ -365,6 +382,13 @@ static int stn_forward(cg_model* m, cg_stn* s, const float* in, int B) {
 // gout, gin: [B,S,S,ch]; gin is written (sum of the sampler branch and the localisation branch, nn.ConcatTable)
 static int stn_backward(cg_model* m, cg_stn* s, const float* gout, float* gin, int B) {
   int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
+  if (s->fused) {
+    float* ggrid = BW(m, (size_t)B * S * S * 2); float* gl1 = BW(m, (size_t)B * 64); NN(ggrid); NN(gl1);
+    float* part = nullptr;
+    if (!m->skip_param_grads) { part = BW(m, (size_t)B * stn_fused_part_floats(ch, s->nth)); NN(part); }
+    StnFusedParams p; StnFusedGrads g; stn_params(m, s, &p, &g);
+    return stn_fused_backward(p, g, s->in, B, s->pool1, s->c1o, s->c2o, s->pool2, s->l1o, s->theta, s->A, gout, gin, ggrid, gl1, part, m->skip_param_grads);
+  }
   float* ggrid = BW(m, (size_t)B * S * S * 2); NN(ggrid);
   CG_TRY(bilinear_bwd(s->in, s->grid, gout, gin, ggrid, B, S, S, ch));
   float* gA = BW(m, (size_t)B * 6); NN(gA); CG_TRY(affine_grid_bwd(ggrid, gA, B, S, S));
@@ -406,6 +430,56 @@ static int ensure_masks(cg_model* d, int B) {
   return CG_OK;
 }
 
+// The same network with every element-wise chain between two convolutions as ONE kernel (fuse_d.cu) and the conv operands cached:
+// conv -> [PReLU -> pool -> SpatialDropout -> fp16 operand of the next conv]; that operand also feeds the next layer's weight gradient.
+static uint8_t* FWQ(cg_model* m, int N, int H, int W, int C, int k) { return (uint8_t*)FW(m, conv_tc_operand_bytes(N, H, W, C, k) / 4); }
+static int conv_packed(cg_model* m, int li, const uint8_t* xq, float* y, int N, int H) {
+  cg_layer& L = m->layers[li];
+  return conv_fwd_tc_packed(xq, L.Wp, L.bp, y, N, H, H, L.s.Ci, L.s.Co, L.s.k);
+}
+static int D_forward_fused(cg_model* d, int B, const float* mk, float* sig_dev, float* pre_dev) {
+  long n64 = (long)B * 1024 * 64;
+  d->tc1 = FW(d, n64); d->tc2 = FW(d, n64); NN(d->tc1); NN(d->tc2);
+  CG_TRY(layer_fwd(d, d->t1, d->stn[0].out, d->tc1, B, 32, 32));                                   // conv C -> 64 (models.lua:646)
+  uint8_t* xq_t2 = FWQ(d, B, 32, 32, 64, 3); NN(xq_t2); d->xq_t2 = xq_t2;
+  CG_TRY(act_pool_mask_pack(d->tc1, d->P + d->t1pw, B, 32, 32, 64, 0, nullptr, 0, nullptr, nullptr, 0, 0, xq_t2, 3));   // PReLU -> operand of conv 64 -> 64 (:647-648)
+  CG_TRY(conv_packed(d, d->t2, xq_t2, d->tc2, B, 32));
+  d->T = FW(d, n64 / 4); NN(d->T);
+  uint8_t* xq_b4 = FWQ(d, B, 16, 16, 64, 5); NN(xq_b4); d->xq_b4 = xq_b4;
+  // PReLU -> AvgPool(2) -> SpatialDropout(0.2) (:649-651): T in fp32 for the three transformers, and as the operand of branch 4's 5x5 conv
+  CG_TRY(act_pool_mask_pack(d->tc2, d->P + d->t2pw, B, 32, 32, 64, 1, mk, 64, nullptr, d->T, 64, 0, xq_b4, 5)); mk += (long)B * 64;
+  d->catd = FW(d, (size_t)B * 20480); NN(d->catd);
+  const float* mk_head = mk + (long)B * (64 * 3 + 128);                                            // SpatialDropout(0.5) after nn.Concat (:695), applied as each branch writes its slot
+  CG_TRY(lanes_fork());
+  for (int b = 0; b < 4; ++b) {
+    LaneScope lane(b); CG_TRY(lane.status);
+    const int Co = b < 3 ? 64 : 128, k2 = b < 3 ? 3 : 7;
+    const long n1 = (long)B * 256 * Co;
+    d->bc1[b] = FW(d, n1); NN(d->bc1[b]);
+    if (b < 3) { CG_TRY(stn_forward(d, &d->stn[b + 1], d->T, B)); CG_TRY(layer_fwd(d, d->b1[b], d->stn[b + 1].out, d->bc1[b], B, 16, 16)); }
+    else CG_TRY(conv_packed(d, d->b1[b], xq_b4, d->bc1[b], B, 16));
+    d->bidx[b] = (uint8_t*)FW(d, n1 / 16 + 4); d->bc2[b] = FW(d, n1 / 4); NN(d->bidx[b]); NN(d->bc2[b]);
+    uint8_t* xq2 = FWQ(d, B, 8, 8, Co, k2); NN(xq2); d->xq_b2[b] = xq2;
+    // PReLU -> MaxPool(2) -> SpatialDropout(0.2) -> operand of the branch's second conv (:656-659, :681-685)
+    CG_TRY(act_pool_mask_pack(d->bc1[b], d->P + d->bpw1[b], B, 16, 16, Co, 2, mk + (long)B * 64 * b, Co, d->bidx[b], nullptr, 0, 0, xq2, k2));
+    CG_TRY(conv_packed(d, d->b2[b], xq2, d->bc2[b], B, 8));
+    // PReLU -> this branch's channel slot of the Concat buffer, SpatialDropout(0.5) of the head applied on the way (:660, :695)
+    CG_TRY(act_pool_mask_pack(d->bc2[b], d->P + d->bpw2[b], B, 8, 8, Co, 0, mk_head + b * 64, 320, nullptr, d->catd, 320, b * 64, nullptr, 0));
+  }
+  CG_TRY(lanes_join());
+  mk = mk_head + (long)B * 320;
+  d->h1o = FW(d, (size_t)B * 256); d->ha1 = FW(d, (size_t)B * 256); d->hd = FW(d, (size_t)B * 256); NN(d->h1o); NN(d->ha1); NN(d->hd);
+  CG_TRY(layer_fwd(d, d->h1, d->catd, d->h1o, B, 1, 1));
+  CG_TRY(prelu_fwd(d->h1o, d->P + d->hpw, d->ha1, (long)B * 256));
+  CG_TRY(mask_elems(d->ha1, mk, d->hd, (long)B * 256));
+  d->h2o = FW(d, B); d->hsig = FW(d, B); NN(d->h2o); NN(d->hsig);
+  CG_TRY(layer_fwd(d, d->h2, d->hd, d->h2o, B, 1, 1));
+  CG_TRY(sigmoid_fwd(d->h2o, d->hsig, B));
+  if (sig_dev) CG_CUDA(cudaMemcpyAsync(sig_dev, d->hsig, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
+  if (pre_dev) CG_CUDA(cudaMemcpyAsync(pre_dev, d->h2o, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
+  return CG_OK;
+}
+
 int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float* pre_dev) {
   CG_TRY(model_repack(d));
   CG_TRY(ensure_masks(d, B));
@@ -415,6 +489,8 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
   CG_TRY(nchw_to_nhwc(x_nchw, d->xin, B, C, 1024));                      // nn.Copy + the STN's nn.Transpose (models.lua:643,870)
   CG_TRY(stn_forward(d, &d->stn[0], d->xin, B));
   long n64 = (long)B * 1024 * 64;
+  d->dfused = ctx().conv_engine == 1 && getenv("CATGEN_D_UNFUSED") == nullptr && conv_tc_cached_ok(32, 32, 64, 64, 3);
+  if (d->dfused) return D_forward_fused(d, B, mk, sig_dev, pre_dev);
   d->tc1 = FW(d, n64); d->ta1 = FW(d, n64); d->tc2 = FW(d, n64); d->ta2 = FW(d, n64); NN(d->tc1); NN(d->ta1); NN(d->tc2); NN(d->ta2);
   CG_TRY(layer_fwd(d, d->t1, d->stn[0].out, d->tc1, B, 32, 32)); CG_TRY(prelu_fwd(d->tc1, d->P + d->t1pw, d->ta1, n64));
   CG_TRY(layer_fwd(d, d->t2, d->ta1, d->tc2, B, 32, 32)); CG_TRY(prelu_fwd(d->tc2, d->P + d->t2pw, d->ta2, n64));
@@ -483,12 +559,12 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
     long n2 = (long)B * 64 * Co, n1 = n2 * 4;
     float* go = BW(d, n2); NN(go); CG_TRY(copy_channels(gcat, go, (long)B * 64, Co, 320, b * 64, 1));
     float* gc2 = BW(d, n2); NN(gc2); CG_TRY(prelu_bwd(d->bc2[b], go, d->P + d->bpw2[b], gc2, PG(d, d->bpw2[b]), n2));
-    float* gdr = BW(d, n2); NN(gdr); CG_TRY(layer_bwd(d, d->b2[b], d->bdr[b], gc2, gdr, B, 8, 8));
+    float* gdr = BW(d, n2); NN(gdr); CG_TRY(layer_bwd(d, d->b2[b], d->dfused ? nullptr : d->bdr[b], gc2, gdr, B, 8, 8, d->dfused ? d->xq_b2[b] : nullptr));
     float* gmp = BW(d, n2); NN(gmp); CG_TRY(mask_channels(gdr, mk, gmp, B, 64, Co)); mk += (long)B * Co;
     float* ga1 = BW(d, n1); NN(ga1); CG_TRY(maxpool2_bwd(gmp, d->bidx[b], ga1, B, 16, 16, Co));
     float* gc1 = BW(d, n1); NN(gc1); CG_TRY(prelu_bwd(d->bc1[b], ga1, d->P + d->bpw1[b], gc1, PG(d, d->bpw1[b]), n1));
     const float* bin = b < 3 ? d->stn[b + 1].out : d->T;
-    float* gbin = BW(d, nT); NN(gbin); CG_TRY(layer_bwd(d, d->b1[b], bin, gc1, gbin, B, 16, 16));
+    float* gbin = BW(d, nT); NN(gbin); CG_TRY(layer_bwd(d, d->b1[b], bin, gc1, gbin, B, 16, 16, (d->dfused && b == 3) ? d->xq_b4 : nullptr));
     if (b < 3) {
       float* gs = BW(d, nT); NN(gs);
       CG_TRY(stn_backward(d, &d->stn[b + 1], gbin, gs, B));
@@ -501,7 +577,7 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   long n64 = (long)B * 1024 * 64;
   float* gta2 = BW(d, n64); NN(gta2); CG_TRY(avgpool2_bwd(gtp, gta2, B, 32, 32, 64));
   float* gtc2 = BW(d, n64); NN(gtc2); CG_TRY(prelu_bwd(d->tc2, gta2, d->P + d->t2pw, gtc2, PG(d, d->t2pw), n64));
-  float* gta1 = BW(d, n64); NN(gta1); CG_TRY(layer_bwd(d, d->t2, d->ta1, gtc2, gta1, B, 32, 32));
+  float* gta1 = BW(d, n64); NN(gta1); CG_TRY(layer_bwd(d, d->t2, d->dfused ? nullptr : d->ta1, gtc2, gta1, B, 32, 32, d->dfused ? d->xq_t2 : nullptr));
   float* gtc1 = BW(d, n64); NN(gtc1); CG_TRY(prelu_bwd(d->tc1, gta1, d->P + d->t1pw, gtc1, PG(d, d->t1pw), n64));
   float* gs0 = BW(d, (size_t)B * 1024 * C); NN(gs0); CG_TRY(layer_bwd(d, d->t1, d->stn[0].out, gtc1, gs0, B, 32, 32));
   float* gin = BW(d, (size_t)B * 1024 * C); NN(gin);

@@ -17,6 +17,7 @@ struct cg_stn {
   // saved activations
   const float* in;
   float *pool1, *c1o, *a1, *c2o, *a2, *pool2, *l1o, *al1, *theta, *A, *grid, *out;
+  bool fused = false;        // the last forward ran stn_fused.cu (theta then has stride 4; a1, a2, al1, grid are not materialised)
 };
 
 struct cg_gstage { int up, Ci, Co, k, bn, layer; long og, obt, opw; };
@@ -50,6 +51,8 @@ struct cg_model {
   long t1pw, t2pw, bpw1[4], bpw2[4], hpw;
   float *xin, *tc1, *ta1, *tc2, *ta2, *tpool, *T, *bc1[4], *ba1[4], *bmp[4], *bdr[4], *bc2[4], *cat, *catd, *h1o, *ha1, *hd, *h2o, *hsig;
   uint8_t* bidx[4];
+  bool dfused = false;                       // the last D forward ran the fused chains (fuse_d.cu): ta1, ta2, tpool, ba1, bmp, bdr, cat are not materialised
+  const uint8_t *xq_t2 = nullptr, *xq_b4 = nullptr, *xq_b2[4] = {nullptr, nullptr, nullptr, nullptr};   // cached conv operands (forward + weight gradient)
   float* masks = nullptr; long masks_n = 0; int masks_B = 0;
   float* mq = nullptr; int mq_count = 0, mq_next = 0, mq_B = 0;   // queued user masks (cg_D_set_masks)
 };
@@ -66,6 +69,16 @@ struct cg_trainer {
 };
 
 namespace cg {
+// fused spatial transformer (stn_fused.cu): parameter / gradient pointers into the flat Torch-layout vectors
+struct StnFusedParams { const float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; int ch, S, rot, scl, trn, nth; };
+struct StnFusedGrads { float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; };
+inline int stn_fused_part_floats(int ch, int nth) { return 16 * ch * 9 + 16 + 16 * 16 * 9 + 16 + 64 + nth * 64 + nth; }
+int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* pool1, float* c1o, float* c2o, float* pool2, float* l1o, float* theta, float* A, float* out);
+int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const float* in, int B, const float* pool1, const float* c1o, const float* c2o, const float* pool2,
+                       const float* l1o, const float* theta, const float* A, const float* gout, float* gin, float* ggrid, float* gl1, float* part, int skip_param_grads);
+// fuse_d.cu: PReLU -> [2x2 pool] -> dropout mask -> {dense fp32 / Concat slot / next conv's fp16 operand} in one pass over a conv output
+int act_pool_mask_pack(const float* y, const float* pw, int N, int H, int W, int C, int pool, const float* mask, int mask_stride, uint8_t* idx,
+                       float* out, int out_stride, int out_off, uint8_t* xq, int k);
 int model_build(cg_model* m);                       // layout + allocation + init
 int model_repack(cg_model* m);                      // refresh packed operands if dirty
 long D_mask_floats(int B);

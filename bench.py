@@ -56,6 +56,13 @@ class Clocks:
         except Exception:
             self.p = None
 
+    def mark(self):
+        """only samples taken from now on count (the sampler is started early so that its start-up is outside the timed region)"""
+        try:
+            self.skip = sum(1 for _ in open(self.f.name))
+        except Exception:
+            self.skip = 0
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -63,7 +70,7 @@ class Clocks:
         self.p.terminate(); self.p.wait()
         self.f.flush(); self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        for line in self.f.read().splitlines()[getattr(self, "skip", 0):]:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 8:
                 continue
@@ -276,18 +283,33 @@ def main():
         lib.check(L.cg_train_step_dev(T.h, C.byref(cfg), real_d + 4 * n_real * i, zd_d + 4 * n_zd * i, zg_d + 4 * n_zg * i,
                                       lib.P(lossD) if want_loss else None, lib.P(lossG) if want_loss else None))
 
+    # the nvidia-smi sampler is started BEFORE the warm-up and given time to produce its first sample: its start-up (NVML init) stalled
+    # launches for tens of ms when it fell inside the timed region (three of seven runs in round 2 showed 10-13 ms/step in this region
+    # against 6.5-7 ms in the unsampled repeat below)
+    clocks = Clocks(local) if (rank == 0 and not os.environ.get("CATGEN_BENCH_NOSMI")) else None
+    if clocks is not None:
+        t_w = time.time()
+        while time.time() - t_w < 5.0 and os.path.getsize(clocks.f.name) == 0:
+            time.sleep(0.05)
     stage("warm-up steps")
     for i in range(W):
-        dev_step(i, False)
+        dev_step(i, i == 0)              # the first warm-up step also reads its loss back: that path is warm before the timed region
         stage("warm-up step %d enqueued" % i)
     barrier()
     stage("timed region")
-    clocks = Clocks(local) if rank == 0 else None
+    if clocks is not None:
+        clocks.mark()
     L.cg_reset_launch_count()
     lib.check(L.cg_timer_start())
     t_wall = time.perf_counter()
+    diag = os.environ.get("CATGEN_BENCH_STEPTIMES")
+    t_steps = []
     for i in range(W, W + K):
         dev_step(i, i == W + K - 1)      # the loss of the last step is read back: the result of the region is consumed
+        if diag:                         # diagnosis only (serialises host and device): where inside the region does the time go
+            lib.check(L.cg_sync()); t_steps.append(time.perf_counter())
+    if diag:
+        sys.stderr.write("[bench steptimes ms] " + " ".join("%.2f" % (1e3 * (b - a)) for a, b in zip([t_wall] + t_steps[:-1], t_steps)) + "\n")
     ms = C.c_float()
     lib.check(L.cg_timer_stop(C.byref(ms)))
     barrier()

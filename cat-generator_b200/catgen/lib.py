@@ -15,6 +15,7 @@ SO_PATH = os.path.join(PKG_DIR, "libcatgen.so")
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "catgen.h")
 
 G32UP, G32UPC, D32_ST3 = 0, 1, 2
+V32 = 3
 fp = C.POINTER(C.c_float)
 
 

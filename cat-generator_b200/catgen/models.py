@@ -117,6 +117,28 @@ class Discriminator(Module):
         check(self.L.cg_D_set_masks(self.h, P(f32(masks)), int(B), int(count)))
 
 
+class Validator(Module):
+    """create_V32 (models.lua:765-804).  Forward only and always in evaluate() mode, the way train.lua:119-123 uses it."""
+
+    def forward(self, x):
+        x = f32(x)
+        B = x.shape[0]
+        out = np.empty((B, 2), np.float32)
+        check(self.L.cg_V_forward(self.h, P(x), B, P(out)))
+        self._B, self.output = B, out
+        return out
+
+    def training(self):
+        raise lib.CatgenError("V is only ever evaluated on this path (train.lua:123); train_v.lua is out of scope")
+
+
+def create_V(dimensions, seed=3):
+    """models.create_V(dimensions), models.lua:716-721 -> create_V32 at 32x32."""
+    if dimensions[1] != 32 or dimensions[2] != 32:
+        raise lib.CatgenError("only create_V32 is built (SURVEY.md section 8 row F3)")
+    return Validator(lib.V32, dimensions[0], 100, seed)
+
+
 def create_G(dimensions, noiseDim, seed=1, kind=None):
     """models.create_G(dimensions, noiseDim), models.lua:234-240.  32x32 -> G32up-c; `kind` selects G32up."""
     if dimensions[1] != 32 or dimensions[2] != 32:

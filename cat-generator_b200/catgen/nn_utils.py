@@ -66,3 +66,10 @@ def switchToTrainingMode(MODEL_G, MODEL_D):
 def switchToEvaluationMode(MODEL_G, MODEL_D):
     """nn_utils.lua:343-349."""
     MODEL_G.evaluate(); MODEL_D.evaluate()
+
+
+def rateWithV(MODEL_V, images):
+    """NN_UTILS.rateWithV (utils/nn_utils.lua:686-711): 1 - mean P(fake) under V; accepts a list of images or one array."""
+    x = np.stack([np.asarray(i, np.float32) for i in images]) if isinstance(images, (list, tuple)) else np.asarray(images, np.float32)
+    predictions = MODEL_V.forward(x)
+    return 1.0 - float(predictions[:, 0].astype(np.float64).mean())

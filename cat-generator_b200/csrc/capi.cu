@@ -227,6 +227,9 @@ int cg_init(int device) {
   { const char* e = getenv("CATGEN_LANES"); c.lanes_on = !(e && e[0] == '0'); }
   { const char* e = getenv("CATGEN_SIDE"); c.side_on = !(e && e[0] == '0'); }
   c.device = device; c.inited = true; c.launches = 0;
+  // the page-locked scratch the loss read-back uses: allocated here, not on the first cg_train_step that asks for a loss (cudaMallocHost took
+  // 1-35 ms there -- profiles/r02_bench_hiccup.txt -- and fell inside whatever region that step belonged to)
+  if (!pinned(4096)) return set_err(CG_ERR_CUDA, "cudaMallocHost failed");
   return CG_OK;
 }
 void cg_shutdown(void) {
@@ -315,7 +318,7 @@ int cg_model_free(cg_model* m) {
   for (auto& L : m->layers) { cg::conv_tc_unregister_wslices(L.Wp); cg::conv_tc_unregister_wslices(L.Wd); }
   if (m->wq) cudaFree(m->wq); if (m->jobs_dev) cudaFree(m->jobs_dev);
   if (m->P) cudaFree(m->P); if (m->G) cudaFree(m->G); if (m->packed) cudaFree(m->packed); if (m->run) cudaFree(m->run);
-  if (m->masks) cudaFree(m->masks); if (m->mq) cudaFree(m->mq); if (m->rng_dev) cudaFree(m->rng_dev);
+  if (m->masks) cudaFree(m->masks); if (m->amax) cudaFree(m->amax); if (m->mq) cudaFree(m->mq); if (m->rng_dev) cudaFree(m->rng_dev);
   for (auto& b : m->fw) b.release(); for (auto& b : m->bw) b.release(); m->gwp.release();
   delete m; return CG_OK;
 }
@@ -327,7 +330,7 @@ int cg_model_get_params(cg_model* m, float* host) {
 int cg_model_set_params(cg_model* m, const float* host) {
   CG_REQUIRE_INIT(); CG_ARG(m && host);
   CG_CUDA(cudaMemcpyAsync(m->P, host, sizeof(float) * m->np, cudaMemcpyHostToDevice, ctx().stream)); CG_CUDA(cudaStreamSynchronize(ctx().stream));
-  m->dirty = true; return CG_OK;
+  m->dirty = true; m->dirty32 = true; return CG_OK;
 }
 int cg_model_get_grads(cg_model* m, float* host) {
   CG_REQUIRE_INIT(); CG_ARG(m && host);
@@ -346,7 +349,7 @@ int cg_model_set_bn_running(cg_model* m, const float* host) {
 int cg_model_set_mode(cg_model* m, int training) { CG_ARG(m); m->training = training ? 1 : 0; return CG_OK; }
 
 int cg_G_forward(cg_model* g, const float* z, int B, float* out) {
-  CG_REQUIRE_INIT(); CG_ARG(g && z && out && B > 0); CG_ARG(g->kind != CG_D32_ST3);
+  CG_REQUIRE_INIT(); CG_ARG(g && z && out && B > 0); CG_ARG(g->kind == CG_G32UP || g->kind == CG_G32UPC);
   size_t nz = (size_t)B * g->nz, no = (size_t)B * g->C * 1024;
   float* st = (float*)workspace2(sizeof(float) * (nz + no)); if (!st) return CG_ERR_CUDA;
   CG_CUDA(cudaMemcpyAsync(st, z, sizeof(float) * nz, cudaMemcpyHostToDevice, ctx().stream));
@@ -355,7 +358,7 @@ int cg_G_forward(cg_model* g, const float* z, int B, float* out) {
   CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
 }
 int cg_G_backward(cg_model* g, const float* gout, float* gz) {
-  CG_REQUIRE_INIT(); CG_ARG(g && gout); CG_ARG(g->kind != CG_D32_ST3);
+  CG_REQUIRE_INIT(); CG_ARG(g && gout); CG_ARG(g->kind == CG_G32UP || g->kind == CG_G32UPC);
   int B = g->B; size_t no = (size_t)B * g->C * 1024, nz = (size_t)B * g->nz;
   float* st = (float*)workspace2(sizeof(float) * (no + nz)); if (!st) return CG_ERR_CUDA;
   CG_CUDA(cudaMemcpyAsync(st, gout, sizeof(float) * no, cudaMemcpyHostToDevice, ctx().stream));
@@ -380,6 +383,15 @@ int cg_D_backward(cg_model* d, const float* gout, float* gx) {
   CG_CUDA(cudaMemcpyAsync(st, gout, sizeof(float) * B, cudaMemcpyHostToDevice, ctx().stream));
   CG_TRY(D_backward_dev(d, st, st + B));
   if (gx) CG_CUDA(cudaMemcpyAsync(gx, st + B, sizeof(float) * nx, cudaMemcpyDeviceToHost, ctx().stream));
+  CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
+}
+int cg_V_forward(cg_model* v, const float* x, int B, float* out) {
+  CG_REQUIRE_INIT(); CG_ARG(v && x && out && B > 0); CG_ARG(v->kind == CG_V32);
+  size_t nx = (size_t)B * v->C * 1024;
+  float* st = (float*)workspace2(sizeof(float) * (nx + 2 * (size_t)B)); if (!st) return CG_ERR_CUDA;
+  CG_CUDA(cudaMemcpyAsync(st, x, sizeof(float) * nx, cudaMemcpyHostToDevice, ctx().stream));
+  CG_TRY(V_forward_dev(v, st, B, st + nx));
+  CG_CUDA(cudaMemcpyAsync(out, st + nx, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, ctx().stream));
   CG_CUDA(cudaStreamSynchronize(ctx().stream)); return CG_OK;
 }
 int cg_D_mask_floats(int B, int64_t* n) { CG_ARG(n && B > 0); *n = D_mask_floats(B); return CG_OK; }
@@ -414,7 +426,7 @@ int cg_penalty_clamp(cg_model* m, float l1, float l2sign, float l2, float clampv
   return T.finish();
 }
 int cg_trainer_create(cg_trainer** out, cg_model* G, cg_model* D) {
-  CG_REQUIRE_INIT(); CG_ARG(out && G && D); CG_ARG(G->kind != CG_D32_ST3 && D->kind == CG_D32_ST3 && G->C == D->C);
+  CG_REQUIRE_INIT(); CG_ARG(out && G && D); CG_ARG((G->kind == CG_G32UP || G->kind == CG_G32UPC) && D->kind == CG_D32_ST3 && G->C == D->C);
   cg_trainer* t = new (std::nothrow) cg_trainer(); if (!t) return set_err(CG_ERR_STATE, "out of host memory");
   t->G = G; t->D = D;
   CG_CUDA(cudaMalloc(&t->mD, sizeof(float) * D->np)); CG_CUDA(cudaMalloc(&t->vD, sizeof(float) * D->np));
@@ -559,7 +571,7 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   // The graph is captured from -- and therefore always replayed from -- a state in which both networks' packed operands are fresh:
   // whatever ran since the last update (an eager forward, cg_model_set_params, a replay that ended with an Adam step) is settled by an
   // eager repack here; the host-side flags are put back to what an eager step leaves behind after every replay (sg->end_dirty_*).
-  CG_TRY(model_repack(t->G)); CG_TRY(model_repack(t->D));
+  { const int need32 = !(conv_tc_all_shapes_taken(c->B) && conv_tc_all_shapes_taken(c->B / 2)); CG_TRY(model_repack(t->G, need32)); CG_TRY(model_repack(t->D, need32)); }
   CG_CUDA(cudaMemcpyAsync(g0, real, sizeof(float) * nr, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr, zD, sizeof(float) * nzd, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyDeviceToDevice, X.stream));
@@ -580,7 +592,7 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
         CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG);
       }
       sg->gen = X.alloc_gen;
-      sg->end_dirty_G = t->G->dirty; sg->end_dirty_D = t->D->dirty;
+      sg->end_dirty_G = t->G->dirty; sg->end_dirty_D = t->D->dirty; sg->end_dirty32_G = t->G->dirty32; sg->end_dirty32_D = t->D->dirty32;
       sg->launches = X.launches - l0; X.launches = l0;      // captured, not executed yet
     }
     if (sg->failed) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
@@ -589,6 +601,7 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   // the replay ran the Adam updates on the device: leave the flags as the eager step would (a network updated after its last forward
   // of the step has stale packed operands for whatever runs next)
   t->G->dirty = sg->end_dirty_G; t->D->dirty = sg->end_dirty_D;
+  t->G->dirty32 = sg->end_dirty32_G; t->D->dirty32 = sg->end_dirty32_D;   // the captured repacks refresh the fp32 fallback operands exactly when the capture step's did
   X.launches += sg->launches;
   return read_losses(t, c, lossD, lossG);
 }

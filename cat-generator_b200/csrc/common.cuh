@@ -51,6 +51,8 @@ struct Ctx {
   // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
   bool prof_on = false;
   double next_flops = 0, next_bytes = 0;
+  int fp32_operands_stale = 0;         // > 0 inside a model executor that skipped refreshing the fp32 fallback operands: a fallback must fail loudly
+  unsigned int* next_amax = nullptr;   // one-shot: the next conv / split-K reduction launch also records max|output| there (atomicMax on float bits; the caller zeroes it)
   struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
   std::vector<ProfRec> prof;
   cudaEvent_t t0 = nullptr, t1 = nullptr;

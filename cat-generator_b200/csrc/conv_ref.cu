@@ -48,17 +48,24 @@ int unpack_wgrad_acc(const float* gWp, float* gW_acc, const ConvSpec& s) {
 }
 
 // ------------------------------------------------------------------ split-K reduction (fixed order)
-__global__ void k_splitk_reduce(const float* __restrict__ part, int S, long n, int ncol, const float* __restrict__ bias, float* __restrict__ out) {
+__global__ void k_splitk_reduce(const float* __restrict__ part, int S, long n, int ncol, const float* __restrict__ bias, float* __restrict__ out, unsigned int* __restrict__ amax) {
+  float mx = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float s = bias ? bias[i % ncol] : 0.f;
     for (int z = 0; z < S; ++z) s += part[(long)z * n + i];
-    out[i] = s;
+    out[i] = s; mx = fmaxf(mx, fabsf(s));
+  }
+  if (amax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(amax, __float_as_uint(mx));
   }
 }
 
 int splitk_reduce(const float* part, int S, long n, int ncol, const float* bias, float* out) {
   ctx().next_bytes = 4.0 * (double)n * (S + 1);
-  CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, part, S, n, ncol, bias, out); return CG_OK;
+  unsigned int* amax = ctx().next_amax; ctx().next_amax = nullptr;
+  CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, part, S, n, ncol, bias, out, amax); return CG_OK;
 }
 
 // ------------------------------------------------------------------ partial sums -> Torch-layout gradient, fused
@@ -211,7 +218,7 @@ static int conv_fwd_ref(const float* x, const float* Wp, const float* bias, floa
   ctx().next_flops = fl; ctx().next_bytes = by;
   if (vec) CG_LAUNCH(k_conv_fwd<true>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
   else CG_LAUNCH(k_conv_fwd<false>, g, 256, 0, x, Wp, bias, dst, M, H, W, Ci, Co, k, Ktot, Kper, S);
-  if (S > 1) { long n = M * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, bias, y); }
+  if (S > 1) { long n = M * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, bias, y, (unsigned int*)nullptr); }
   return CG_OK;
 }
 
@@ -301,7 +308,7 @@ static int conv_wgrad_ref(const float* x, const float* gy, float* gWp_out, int N
   ctx().next_flops = 2.0 * (double)M * Co * Ktot; ctx().next_bytes = 4.0 * ((double)M * Ci + (double)M * Co + (double)Ktot * Co);
   if (vec) CG_LAUNCH(k_conv_wgrad<true>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
   else CG_LAUNCH(k_conv_wgrad<false>, g, 256, 0, x, gy, dst, M, H, W, Ci, Co, k, Ktot, Mper);
-  if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out); }
+  if (S > 1) { long n = (long)Ktot * Co; CG_LAUNCH(k_splitk_reduce, grid1d(n, 256, 2), 256, 0, dst, S, n, Co, (const float*)nullptr, gWp_out, (unsigned int*)nullptr); }
   if (gW_acc && parts_to_torch_acc(gWp_out, 1, 0, gW_acc, Ci, Co, k * k) == CG_OK) { if (done) *done = 1; }
   return CG_OK;
 }
@@ -316,6 +323,8 @@ void conv_tc_set_gradient_operands(int on);   // tf32 operands for gradient-valu
 
 int conv_fwd(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   if (ctx().conv_engine == 1) { int s = conv_fwd_tc(x, Wp, bias, y, N, H, W, Ci, Co, k); if (s != CG_ERR_UNSUPPORTED) return s; }
+  if (ctx().fp32_operands_stale)
+    return set_err(CG_ERR_STATE, "conv %dx%d %d->%d k=%d at batch %d fell back to the fp32 kernel, whose operands were not refreshed (model_repack need32)", H, W, Ci, Co, k, N);
   return conv_fwd_ref(x, Wp, bias, y, N, H, W, Ci, Co, k);
 }
 int conv_dgrad(const float* gy, const float* Wd, float* gx, int N, int H, int W, int Ci, int Co, int k) {

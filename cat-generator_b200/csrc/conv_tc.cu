@@ -274,21 +274,23 @@ __device__ __forceinline__ void pack_slices_job(const float* __restrict__ W, uin
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
 }
-__global__ void k_repack_model(const PackJob* __restrict__ jobs, int njobs) {
+// mode bit 0: the fp32 operands Wp / Wd (only the CUDA-core fallback kernels read them) ; bit 1: bias + the fp16 weight slices of both directions
+__global__ void k_repack_model(const PackJob* __restrict__ jobs, int njobs, int mode) {
   int j = 0;
   while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].blk0) ++j;
   const PackJob J = jobs[j];
   const ConvSpec s = J.s;
   const long tid = (blockIdx.x - J.blk0) * (long)blockDim.x + threadIdx.x, nth = (long)J.nblk * blockDim.x;
   const long n = (long)s.k * s.k * s.Ci * s.Co;
-  for (long i = tid; i < n; i += nth) {     // Wp[(ky,kx,ci)][co]
+  if (mode & 1) for (long i = tid; i < n; i += nth) {     // Wp[(ky,kx,ci)][co]
     int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
     J.Wp[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)];
   }
-  if (J.need_dgrad) for (long i = tid; i < n; i += nth) {     // Wd[(ky,kx,co)][ci], taps flipped
+  if ((mode & 1) && J.need_dgrad) for (long i = tid; i < n; i += nth) {     // Wd[(ky,kx,co)][ci], taps flipped
     int ci = (int)(i % s.Ci); long r = i / s.Ci; int co = (int)(r % s.Co); int tap = (int)(r / s.Co);
     J.Wd[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, s.k - 1 - tap / s.k, s.k - 1 - tap % s.k, ci, co)];
   }
+  if (!(mode & 2)) return;
   for (long cop = tid; cop < s.Co; cop += nth) {
     int Cov = s.Co / s.out_hw;
     J.bp[cop] = J.b[s.out_hw == 1 ? (int)cop : (int)(cop % Cov) * s.out_hw + (int)(cop / Cov)];
@@ -296,8 +298,8 @@ __global__ void k_repack_model(const PackJob* __restrict__ jobs, int njobs) {
   if (J.wqf) pack_slices_job(J.W, J.wqf, s, 0, J.CBf, tid, nth);
   if (J.wqd) pack_slices_job(J.W, J.wqd, s, 1, J.CBd, tid, nth);
 }
-int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks) {
-  CG_LAUNCH(k_repack_model, total_blocks, 256, 0, jobs_dev, njobs);
+int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks, int mode) {
+  CG_LAUNCH(k_repack_model, total_blocks, 256, 0, jobs_dev, njobs, mode);
   return CG_OK;
 }
 
@@ -620,6 +622,7 @@ struct PsParams {
   int ncb, kk, nslices;                // 32-channel blocks that hold data, taps, ncb * kk
   int tiles_x, tiles_y, ntiles;
   int NB, S, D;                        // columns per CTA, weight ring depth, stagger / gap in slices
+  unsigned int* amax_out;              // optional: max|y| over the launch (atomicMax on float bits), the packing-scale bound of the next backward stage
   long long* dbg;                      // experiments (CATGEN_PS_DBG=1): per-CTA clock64 breakdown, 32 values per CTA
   int Z;                               // > 1: K-SPLIT mode (nn.Linear, kk = 1): gridDim.x = Z CTAs each stream their share of the slices for ALL tiles
                                        //      (<= 4) and write raw partial sums to y[z][...] (bias / reduction in k_splitk_reduce)
@@ -639,8 +642,36 @@ __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restri
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
 }
+// ---- CTA-pair (cta_group::2) helpers; mechanics established by tools/tc_pair_probe.cu on B200 (profiles/r02_pair_probe.txt)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r; }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory"); }
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+// tiled TMA whose completion is signalled on a barrier given as a shared::cluster address (the pair leader's)
+__device__ __forceinline__ void tma_2d_bar(void* dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tma_patch_4d_bar(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
 
+// PAIR = 1: the kernel runs as clusters of two CTAs (one TPC) driving ONE tcgen05.mma.cta_group::2 stream: M = 256 = the two CTAs' pixel
+// tiles, N = NB with each CTA holding HALF of every weight slice (NB/2 columns) in its own shared memory.  Why: an M = 128 x N = 128 MMA reads
+// 4 KB of A and 4 KB of B from shared memory per 64 cycles = 128 B/cycle, the whole shared-memory port, so every TMA write and every
+// epilogue staging access steals tensor-pipe time (measured: 352k cycles per CTA against an MMA floor of 177k with weights, patches and TMEM
+// all waiting on the pipe; gpurun_out/r02_e_conv3_dbg.txt).  In pair mode a CTA reads 4 KB + 2 KB per 64 cycles: a quarter of the port is
+// free again.  The leader CTA (rank 0) issues every MMA and commits with multicast; both CTAs load (their TMA completions are counted on
+// the LEADER's barriers), both drain their own TMEM lanes.
+template <int PAIR>
 __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_wfull[16], bar_wempty[16], bar_pfull[PS_SLOTS][2], bar_pempty[PS_SLOTS][2], bar_acc[PS_SLOTS], bar_tfree[PS_SLOTS];
@@ -650,13 +681,16 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
   uint8_t* wring = smem + (size_t)2 * PS_SLOTS * P.patch_bytes;        // S weight slices
   float* stage0 = reinterpret_cast<float*>(wring + (size_t)P.S * P.slice_bytes);   // epilogue staging, 4 warps x 32 rows x 36 floats
 
-  const int gx = gridDim.x, co0 = blockIdx.y * P.NB;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                 // 0 = leader of the pair
+  const int gx = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x, bx = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-column of the grid: CTAs, or pairs
+  const int co0 = blockIdx.y * P.NB;
+  const int ntu = PAIR ? (P.ntiles + 1) / 2 : P.ntiles;               // scheduling units: tiles, or tile pairs (2u + rank)
   long long* dbg = P.dbg ? P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
   const long long t_start = dbg ? clock64() : 0;
   const bool zs = P.Z > 1;                                            // K-split mode
   const int s_begin = zs ? (int)((long)P.nslices * blockIdx.x / P.Z) : 0;                       // first slice this CTA streams
   const int ns = zs ? (int)((long)P.nslices * (blockIdx.x + 1) / P.Z) - s_begin : P.nslices;    // slices per tile cycle (>= 1: Z <= nslices)
-  const int nt = zs ? P.ntiles : (P.ntiles - (int)blockIdx.x + gx - 1) / gx;   // tiles of this CTA (>= 1: the host keeps gridDim.x <= ntiles)
+  const int nt = zs ? P.ntiles : (ntu - bx + gx - 1) / gx;            // tiles of this CTA (>= 1: the host keeps the grid <= the units)
   const int D = zs ? 0 : P.D, kk = P.kk;
   const int ncb = zs ? ns : P.ncb;                                    // 32-channel blocks in this CTA's stream (kk = 1 in K-split mode)
   // slot j owns tiles j, j+4, ...; its k-th tile is accumulated over slices [j*D + k*(ns+D), +ns)
@@ -670,21 +704,30 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
     for (int i = 0; i < P.S; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], PS_SLOTS); }
     for (int j = 0; j < PS_SLOTS; ++j) {
       for (int b = 0; b < 2; ++b) { mbar_init(&bar_pfull[j][b], 1); mbar_init(&bar_pempty[j][b], 1); }
-      mbar_init(&bar_acc[j], 1); mbar_init(&bar_tfree[j], 4);
+      mbar_init(&bar_acc[j], 1); mbar_init(&bar_tfree[j], PAIR ? 8 : 4);   // pair: the leader's issuer waits for BOTH CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   int ncols = 32; while (ncols < PS_SLOTS * P.NB) ncols <<= 1;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                         // the peer's barriers and TMEM exist before anything reaches across
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_base_s;
+  // the i-th tile of this CTA; in pair mode unit u = bx + i*gx holds tiles 2u (leader) and 2u+1 (peer) -- an odd tile count leaves the
+  // last peer a GHOST tile: it recomputes the last real tile (so that every load and barrier stays symmetric) and stores nothing
+  auto tile_id = [&](int i) { return zs ? i : (PAIR ? 2 * (bx + i * gx) + (int)rank : bx + i * gx); };
   auto tile_xy = [&](int i, int& n, int& y0, int& x0) {
-    int t = zs ? i : (int)blockIdx.x + i * gx; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
+    int t = tile_id(i); if (t >= P.ntiles) t = P.ntiles - 1; int tx = t % P.tiles_x; t /= P.tiles_x; int ty = t % P.tiles_y; n = t / P.tiles_y; x0 = tx * 8; y0 = ty * 16;
   };
 
   if (warp == 8) {
@@ -696,8 +739,13 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
         if (dbg) tq = clock64();
         mbar_wait(&bar_wempty[st], ph ^ 1);
         if (dbg) tw += clock64() - tq;
-        mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
-        tma_2d(wring + (size_t)st * P.slice_bytes, &tmw, co0 * 2, (s_begin + s) * 4, &bar_wfull[st]);   // ONE tiled TMA per slice, column block included
+        if (PAIR) {   // each CTA fetches ITS half of the slice's columns; both completions are counted on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&bar_wfull[st], 2 * P.slice_bytes);
+          tma_2d_bar(wring + (size_t)st * P.slice_bytes, &tmw, (co0 + (int)rank * (P.NB / 2)) * 2, (s_begin + s) * 4, mapa_u32(smem_u32(&bar_wfull[st]), 0));
+        } else {
+          mbar_expect_tx(&bar_wfull[st], P.slice_bytes);
+          tma_2d(wring + (size_t)st * P.slice_bytes, &tmw, co0 * 2, (s_begin + s) * 4, &bar_wfull[st]);   // ONE tiled TMA per slice, column block included
+        }
         if (++s == ns) s = 0;
         if (++st == P.S) { st = 0; ph ^= 1u; }
       }
@@ -728,9 +776,14 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
         cb += s_begin;                                                        // K-split (kk = 1): slices ARE channel blocks
         const int buf = cj[j] & 1; const uint32_t ph = (uint32_t)(cj[j] >> 1) & 1u;
         mbar_wait(&bar_pempty[j][buf], ph ^ 1);
-        mbar_expect_tx(&bar_pfull[j][buf], P.patch_bytes);
         int n, y0, x0; tile_xy(j + PS_SLOTS * kj[j], n, y0, x0);
-        tma_patch_4d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, &bar_pfull[j][buf]);
+        if (PAIR) {
+          if (rank == 0) mbar_expect_tx(&bar_pfull[j][buf], 2 * P.patch_bytes);
+          tma_patch_4d_bar(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, mapa_u32(smem_u32(&bar_pfull[j][buf]), 0));
+        } else {
+          mbar_expect_tx(&bar_pfull[j][buf], P.patch_bytes);
+          tma_patch_4d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, &bar_pfull[j][buf]);
+        }
         e2[j] = e1[j]; e1[j] = gj[j] + len; gj[j] += len; cj[j]++;
         if (++qj[j] == nseg) { qj[j] = 0; kj[j]++; gj[j] = j * D + kj[j] * (ns + D); }
       }
@@ -738,11 +791,11 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
   } else if (warp >= 4 && warp < 8) {
     // ===== MMA issuer of slot j = warp - 4.  EVERY issuer walks the whole slice stream and arrives on every slice's "empty"
     // barrier (count 4) -- with a commit behind its MMAs while its slot is accumulating, with a plain arrive otherwise.
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const int j = warp - 4;
       const int nk = (nt - j + PS_SLOTS - 1) / PS_SLOTS;
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t b_lbo = (uint32_t)P.NB * 16;
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P.NB >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+      const uint32_t b_lbo = (uint32_t)(PAIR ? P.NB / 2 : P.NB) * 16;     // pair: the descriptor describes the LOCAL half of B, the instruction the full N
       const uint32_t a_hi = desc_hi((uint32_t)Wp * 16), b_hi = desc_hi(128);
       const uint32_t plane16 = plane_bytes >> 4, slice16 = P.slice_bytes >> 4;
       const uint32_t a_kstep = 2 * plane16, b_kstep = 2 * (b_lbo >> 4);
@@ -773,7 +826,8 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
             p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
             acc = 0;
           } else if (tap == 0 && ncb > 1) {                 // next 32-channel block: hand the buffer back, take the other one
-            umma_commit(&bar_pempty[j][seg & 1]); ++seg;
+            if (PAIR) umma_commit_pair(&bar_pempty[j][seg & 1]); else umma_commit(&bar_pempty[j][seg & 1]);
+            ++seg;
             if (dbg) tq = clock64();
             mbar_wait(&bar_pfull[j][seg & 1], (uint32_t)(seg >> 1) & 1u);
             if (dbg) t_pf += clock64() - tq;
@@ -781,18 +835,26 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
             p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
           }
           const uint32_t a_lo = p_lo + (uint32_t)(ky * Wp + kx), w_lo = w_lo0 + st * slice16;
-          umma<2>(tm, desc64(a_lo, a_hi), desc64(w_lo, b_hi), idesc, acc);
-          umma<2>(tm, desc64(a_lo + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+          if (PAIR) {
+            umma_pair(tm, desc64(a_lo, a_hi), desc64(w_lo, b_hi), idesc, acc);
+            umma_pair(tm, desc64(a_lo + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+          } else {
+            umma<2>(tm, desc64(a_lo, a_hi), desc64(w_lo, b_hi), idesc, acc);
+            umma<2>(tm, desc64(a_lo + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
+          }
           acc = 1u;
           if (++kx == k) { kx = 0; ++ky; }
           if (++tap == kk) { tap = 0; ky = 0; kx = 0; }
           if (g == g0 + ns - 1) {                           // the tile's K cycle is complete
-            umma_commit(&bar_pempty[j][seg & 1]); ++seg;
-            umma_commit(&bar_acc[j]);
-            ++kt; g0 += ns + D;
+            if (PAIR) { umma_commit_pair(&bar_pempty[j][seg & 1]); umma_commit_pair(&bar_acc[j]); }
+            else { umma_commit(&bar_pempty[j][seg & 1]); umma_commit(&bar_acc[j]); }
+            ++seg; ++kt; g0 += ns + D;
           }
-          umma_commit(&bar_wempty[st]);                     // arrives when the MMAs reading this slice have retired
-        } else mbar_arrive(&bar_wempty[st]);
+          if (PAIR) umma_commit_pair(&bar_wempty[st]); else umma_commit(&bar_wempty[st]);   // arrives when the MMAs reading this slice have retired
+        } else {
+          mbar_arrive(&bar_wempty[st]);
+          if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(&bar_wempty[st]), 1));   // the peer's producer counts the same four arrivals per slice
+        }
         if (++st == (uint32_t)S) { st = 0; wph ^= 1u; }
       }
       if (dbg) { dbg[4 + j * 4] = t_wf; dbg[5 + j * 4] = t_pf; dbg[6 + j * 4] = t_tf; dbg[7 + j * 4] = clock64() - t_start; }
@@ -805,6 +867,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
     float* stage = stage0 + warp * (32 * 36);
     const bool wide = vec && (P.NB & 31) == 0;
     long long t_acc = 0, tq = 0;
+    float amx = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int j = i & (PS_SLOTS - 1), kt = i >> 2;
       if (dbg) tq = clock64();
@@ -813,6 +876,8 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;");
       int n, y0, x0; tile_xy(i, n, y0, x0);
       if (zs) n += (int)blockIdx.x * P.N;                                   // partial sums of split z live in y[z]
+      const bool ghost = PAIR && tile_id(i) >= P.ntiles;                    // odd tile count: the last peer tile duplicates a real one -- read TMEM, store nothing
+      const int Hst = ghost ? 0 : P.H;                                      // (every store below is guarded by oy < Hst)
       const uint32_t tcol = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * P.NB);
       if (wide) {
         for (int c0 = 0; c0 < P.NB; c0 += 32) {
@@ -833,6 +898,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
               o.z = __uint_as_float(v[q + 2]) * inv + (P.bias ? P.bias[co0 + c0 + q + 2] : 0.f);
               o.w = __uint_as_float(v[q + 3]) * inv + (P.bias ? P.bias[co0 + c0 + q + 3] : 0.f);
               *reinterpret_cast<float4*>(stage + lane * 36 + q) = o;
+              amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));   // rows past the image are zero operands -> zero outputs
             }
             __syncwarp();
             const int q4 = (lane & 7) * 4;
@@ -841,12 +907,12 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
               const int pl = r * 4 + (lane >> 3), mm = warp * 32 + pl;
               const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
               float4 o = *reinterpret_cast<const float4*>(stage + pl * 36 + q4);
-              if (oy < P.H && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q4) = o;
+              if (oy < Hst && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q4) = o;
             }
             __syncwarp();
           } else {                                          // padded columns past Cout
             const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-            if (oy < P.H && ox < P.W) {
+            if (oy < Hst && ox < P.W) {
               float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
               for (int q = 0; q < 32; ++q) { int co = co0 + c0 + q; if (co < P.Cor) out[c0 + q] = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co] : 0.f); }
             }
@@ -854,7 +920,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
         }
       } else {
         const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-        const bool valid = oy < P.H && ox < P.W;
+        const bool valid = oy < Hst && ox < P.W;
         float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
         for (int c0 = 0; c0 < P.NB; c0 += 16) {
           uint32_t v[16];
@@ -872,6 +938,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
               o.z = __uint_as_float(v[q + 2]) * inv + (P.bias ? P.bias[co0 + c0 + q + 2] : 0.f);
               o.w = __uint_as_float(v[q + 3]) * inv + (P.bias ? P.bias[co0 + c0 + q + 3] : 0.f);
               *reinterpret_cast<float4*>(out + c0 + q) = o;
+              amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
             }
           } else if (valid) {                               // ragged Cout (1, 3): only the real columns exist in y
 #pragma unroll
@@ -882,19 +949,30 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
       // the slot's columns may be overwritten by its next tile
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tfree[j]);
+      if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(&bar_tfree[j]), 0)); else mbar_arrive(&bar_tfree[j]); }
+    }
+    if (P.amax_out) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+      if (lane == 0 && amx > 0.f) atomicMax(P.amax_out, __float_as_uint(amx));
     }
     if (dbg && tid == 0) { dbg[20] = t_acc; dbg[21] = clock64() - t_start; dbg[22] = nt; dbg[23] = total_g; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                                         // nobody leaves while the peer may still be reached (remote arrives, the leader's MMAs reading this CTA's operands)
   if (dbg && tid == 0) dbg[0] = clock64() - t_start;
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+  if (warp == 0) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols));
+  }
 }
 
 static bool conv_v1() { static const bool v = getenv("CATGEN_CONV_V1") != nullptr; return v; }   // the round-1 kernel, kept for A/B measurements
 
+static bool linear_shape_ok(int B);
 // Zmax > 1: the caller allows a K split (nn.Linear: k = 1, at most four tiles); the partial sums go through workspace #1.
+bool conv_tc_all_shapes_taken(int B) { return ctx().conv_engine == 1 && !conv_v1() && getenv("CATGEN_DGRAD_TF32") == nullptr && linear_shape_ok(B); }
 static int conv_ps_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
                        const uint8_t* xq_prepacked, int Zmax = 1) {
   const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // operand padding of the packed activations (shared with the weight gradient)
@@ -903,7 +981,11 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   int NB = Co > 128 ? 128 : Co; while (NB >= 16 && Co % NB) NB -= 16;
   if (NB < 16) return CG_ERR_UNSUPPORTED;
   const int ncb = (Cir + 31) / 32;
-  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * NB * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
+  // CTA pairs (cta_group::2) where the layer needs no K split: each CTA then holds half of every slice
+  static const int pair_env = getenv("CATGEN_PS_PAIR") ? atoi(getenv("CATGEN_PS_PAIR")) : 0;   // off until the pair path has passed the parity suite on the GPU
+  const int ntiles_pre = N * (W / 8) * ((H + 15) / 16);
+  const bool pair = pair_env && Zmax == 1 && NB >= 32 && ntiles_pre >= 2 && (ctx().sm_count % 2) == 0;
+  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * (pair ? NB / 2 : NB) * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
   const size_t budget = 224 * 1024;   // opt-in limit 227 KB per block minus the static part (barriers + 1 KB reserved: cuobjdump -res-usage says 1536 B)
   if (2 * PS_SLOTS * patch_bytes + stage_bytes + 3 * slice_bytes > budget) return CG_ERR_UNSUPPORTED;
   int S = (int)((budget - 2 * PS_SLOTS * patch_bytes - stage_bytes) / slice_bytes); if (S > 16) S = 16;
@@ -933,6 +1015,8 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
     Z = ctx().sm_count / (Co / NB); if (Z > Zmax) Z = Zmax; if (Z > P.nslices / 2) Z = P.nslices / 2; if (Z < 1) Z = 1;
   }
   P.Z = Z;
+  P.amax_out = nullptr;
+  if (Z == 1) { P.amax_out = ctx().next_amax; ctx().next_amax = nullptr; }     // with a K split the final values come out of splitk_reduce, which takes it
   float* part = nullptr;
   if (Z > 1) {
     part = (float*)workspace(sizeof(float) * (size_t)Z * N * H * W * Cor + 256); if (!part) return CG_ERR_CUDA;
@@ -944,9 +1028,15 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   P.patch_bytes = (uint32_t)patch_bytes; P.slice_bytes = (uint32_t)slice_bytes;
   const size_t smem = 2 * PS_SLOTS * patch_bytes + (size_t)S * slice_bytes + stage_bytes;
   static bool attr_done = false;
-  if (!attr_done) { CG_CUDA(cudaFuncSetAttribute(k_conv_ps, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_done = true; }
+  if (!attr_done) {
+    CG_CUDA(cudaFuncSetAttribute(k_conv_ps<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CG_CUDA(cudaFuncSetAttribute(k_conv_ps<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr_done = true;
+  }
   const int gy = Co / NB;
   int gx = ctx().sm_count / gy; if (gx < 1) gx = 1;
+  if (pair) { const int units = (ntiles + 1) / 2; int pairs = gx / 2; if (pairs < 1) pairs = 1; if (pairs > units) pairs = units; gx = 2 * pairs; }
+  else
   // Fill the machine first: measured (gpurun_out/r02_e_layers.txt vs r02_d_layers_v1.txt), insisting on four tiles per CTA left most SMs
   // idle on the 8x8 / 16x16 layers (128 -> 128 7x7 at 8x8: 32 CTAs, 117 us against 52 us with 64 CTAs) -- the tensor pipe, not the
   // weight stream, bounds a CTA, so sharing slices among fewer, busier CTAs buys nothing there.
@@ -957,13 +1047,23 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx, tmw;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
-  CG_TRY(make_wslice_tmap(&tmw, wq, Co, (long)P.nslices * 4, NB));
+  CG_TRY(make_wslice_tmap(&tmw, wq, Co, (long)P.nslices * 4, pair ? NB / 2 : NB));
   static const bool dbg_on = getenv("CATGEN_PS_DBG") != nullptr;
   static long long* dbg_buf = nullptr;
   if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, sizeof(long long) * 32 * 1024);
   P.dbg = (dbg_on && (long)gx * gy <= 1024) ? dbg_buf : nullptr;
   if (P.dbg) cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 32 * 1024, ctx().stream);
-  CG_LAUNCH(k_conv_ps, grid, 320, smem, P, tmx, tmw);
+  if (pair) {   // cluster of two CTAs along x = one TPC
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem; cfg.stream = ctx().stream;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (ctx().prof_on) prof_begin("k_conv_ps<pair>");
+    cudaError_t le = cudaLaunchKernelEx(&cfg, k_conv_ps<1>, P, tmx, tmw);
+    if (ctx().prof_on) prof_end();
+    ctx().next_flops = 0; ctx().next_bytes = 0; ctx().launches++;
+    if (le != cudaSuccess) return set_err(CG_ERR_CUDA, "%s:%d cluster launch k_conv_ps<1> -> %s", __FILE__, __LINE__, cudaGetErrorString(le));
+  } else
+  CG_LAUNCH(k_conv_ps<0>, grid, 320, smem, P, tmx, tmw);
   if (P.dbg) {   // experiments only: where does a CTA's time go (cycles, mean over CTAs)
     cudaStreamSynchronize(ctx().stream);
     size_t n = (size_t)gx * gy;
@@ -1077,6 +1177,7 @@ void conv_tc_set_gradient_operands(int on) { g_tc_grad_operands = on; }
 __global__ void k_absmax(const float* __restrict__ x, long n, unsigned int* __restrict__ out);
 __global__ void k_make_scale(const unsigned int* __restrict__ amax, float* __restrict__ scale2);
 
+int absmax_into(const float* x, long n, unsigned int* amax) { CG_LAUNCH(k_absmax, grid1d(n, 256, 8), 256, 0, x, n, amax); return CG_OK; }
 static float* tc_scale_scratch() {   // per lane: [scale, 1/scale, amax bits, amax bits (fused path, kept zero between uses)]; its own allocation, workspace3 may be regrown by the run
   static float* p[Ctx::kLanes + 1] = {nullptr};
   float*& q = p[ctx().lane + 1];
@@ -1432,6 +1533,26 @@ int conv_wgrad_tc(const float* x, const float* gy, float* gWp_out, int N, int H,
 
 // Whole backward of one conv layer: weight gradient AND input gradient from ONE packed gradient operand.
 //   gWp_out[(tap,ci)][co] (overwritten) ; gx[N,H,W,Ci] = conv(gy, Wd)
+// Backward of one conv layer from a gradient operand that is ALREADY packed (fuse_d.cu: act_bwd_pack wrote gq and its scale): weight
+// gradient chain on the side stream straight into the Torch-layout gradient, input gradient on the issuing stream.  x / xq: the layer's
+// input (fp32, packed here) or its cached operand.  gx may be null (no input gradient wanted); gW_acc null skips the weight gradient.
+int conv_bwd_tc_gq(const float* x, const uint8_t* xq_prepacked, const uint8_t* gq, const float* scale2, const float* Wd, float* gx,
+                   int N, int H, int W, int Ci, int Co, int k, float* gW_acc) {
+  if (!wgrad_shape_ok(H, W, Ci, k) || !tc_shape_ok(H, W, Co, Ci, k, 2) || conv_v1()) return CG_ERR_UNSUPPORTED;
+  GradOperand g; g.gq = gq; g.scale2 = scale2; g.Cg = ((Co + 63) / 64) * 64;
+  if (gW_acc) {
+    const int side = side_begin();
+    int wdone = 0;
+    float* gWp = (float*)workspace(sizeof(float) * (size_t)k * k * Ci * Co + 256);
+    int wst = gWp ? conv_wgrad_tc_impl(x, g, gWp, N, H, W, Ci, Co, k, gW_acc, &wdone, xq_prepacked) : CG_ERR_CUDA;
+    if (wst == CG_OK && !wdone) wst = set_err(CG_ERR_STATE, "weight gradient was not accumulated");
+    if (side) { int est = side_end(); if (wst == CG_OK) wst = est; }
+    CG_TRY(wst);
+  }
+  if (!gx) { ctx().next_amax = nullptr; return CG_OK; }
+  return conv_tc_run<2>(nullptr, Wd, nullptr, gx, N, H, W, Co, Ci, k, scale2, gq);
+}
+
 int conv_bwd_tc(const float* x, const float* gy, const float* Wd, float* gWp_out, float* gx, int N, int H, int W, int Ci, int Co, int k, float* gW_acc, int* done,
                 const uint8_t* xq_prepacked, float* gb_acc, int* bias_done) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;

@@ -108,3 +108,147 @@ int act_pool_mask_pack(const float* y, const float* pw, int N, int H, int W, int
 }
 
 }  // namespace cg
+
+namespace cg {
+
+// ======================================================================================================================
+// Backward.  Per convolution output y the reference chain is  (upstream gradient) -> SpatialDropout' -> pool' -> PReLU'  followed by the
+// layer's accGradParameters / updateGradInput.  One kernel computes gc = dL/dy from the upstream gradient(s) and emits everything the
+// rest of the layer's backward needs in the same pass:
+//   * the fp16 gradient OPERAND of the two backward convolutions (blocked / zero-padded, multiplied by a per-tensor power of two);
+//   * per-(image, 8-channel plane) partial sums of the bias gradient and of PReLU's weight gradient (fixed-order finalize below).
+// The packing scale cannot wait for max|gc| (that would be a second pass): it is derived from max|upstream|, which the PRODUCER of the
+// upstream gradient records for free in its epilogue (conv_tc.cu amax_out, stn_fused.cu) -- |gc| <= sum_i max|g_i| * max(1, |slope|)
+// (* 1/4 behind an average pool), so the scale is at most a few binades more conservative than round 1's exact one: fp16 keeps 10 bits
+// of mantissa either way and nothing can overflow.
+struct ActBwdArgs {
+  const float* g[4]; int ng, g_stride, g_off;   // upstream gradient(s) [N,Hu,Wu,g_stride] at channel offset g_off, summed in index order (nn.Concat's backward order)
+  const float* mask; int mask_stride;            // dropout multipliers [N][mask_stride] (pointer already offset) or null
+  int pool; const uint8_t* idx;                  // 0 none / 1 average / 2 max (argmax bytes [N,Hu,Wu,C])
+  const float *y, *pw;                           // conv output = PReLU input [N,H,W,C]; slope (device scalar)
+  int N, H, W, C;
+  const unsigned int* amax[4];                   // max|g[i]| as float bits
+  float* scale2;                                 // out: [scale, 1/scale]
+  uint8_t* gq; int p, Hq, Wq;                    // packed operand for the layer's k x k backward convolutions
+  double* part;                                  // [N * C/8][9]; null: parameter gradients are not wanted
+};
+
+__global__ void __launch_bounds__(256) k_act_bwd(ActBwdArgs a) {
+  __shared__ double red[9][8];
+  const int c = blockIdx.x, tid = threadIdx.x, C = a.C, Cq = C / 8;
+  const long n = blockIdx.y;
+  const float slope = *a.pw;
+  float bound = 0.f;
+  for (int i = 0; i < a.ng; ++i) bound += __uint_as_float(*a.amax[i]);
+  bound *= fmaxf(1.f, fabsf(slope));
+  if (a.pool == 1) bound *= 0.25f;
+  float sc = 1.f;
+  if (bound > 0.f && isfinite(bound)) sc = exp2f(floorf(log2f(16384.f / bound)));
+  if (!(sc > 0.f) || !isfinite(sc)) sc = 1.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { a.scale2[0] = sc; a.scale2[1] = 1.f / sc; }
+  const int Hu = a.pool ? a.H / 2 : a.H, Wu = a.pool ? a.W / 2 : a.W;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}; float ps = 0.f;
+  uint4* dst = reinterpret_cast<uint4*>(a.gq) + (n * Cq + c) * (long)a.Hq * a.Wq;
+  for (int i = tid; i < a.Hq * a.Wq; i += blockDim.x) {
+    const int yy = i / a.Wq, xx = i - yy * a.Wq, oy = yy - a.p, ox = xx - a.p;
+    uint4 packed = make_uint4(0, 0, 0, 0);
+    if (oy >= 0 && oy < a.H && ox >= 0 && ox < a.W) {
+      const int yu = a.pool ? oy >> 1 : oy, xu = a.pool ? ox >> 1 : ox;
+      const long uo = ((n * Hu + yu) * Wu + xu);
+      float g[8];
+      {
+        const float* s = a.g[0] + uo * a.g_stride + a.g_off + c * 8;
+        float4 v0 = *reinterpret_cast<const float4*>(s), v1 = *reinterpret_cast<const float4*>(s + 4);
+        g[0] = v0.x; g[1] = v0.y; g[2] = v0.z; g[3] = v0.w; g[4] = v1.x; g[5] = v1.y; g[6] = v1.z; g[7] = v1.w;
+      }
+      if (a.ng > 1) {   // gT = ((((0 + p0) + p1) + p2) + p3): the order nn.Concat's backward adds the branches in
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f + g[j];
+        for (int q = 1; q < a.ng; ++q) {
+          const float* s = a.g[q] + uo * a.g_stride + a.g_off + c * 8;
+          float4 v0 = *reinterpret_cast<const float4*>(s), v1 = *reinterpret_cast<const float4*>(s + 4);
+          g[0] += v0.x; g[1] += v0.y; g[2] += v0.z; g[3] += v0.w; g[4] += v1.x; g[5] += v1.y; g[6] += v1.z; g[7] += v1.w;
+        }
+      }
+      if (a.mask) {
+        const float* mk = a.mask + n * a.mask_stride + c * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= mk[j];
+      }
+      if (a.pool == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+      } else if (a.pool == 2) {
+        const uint2 w = *reinterpret_cast<const uint2*>(a.idx + uo * C + c * 8);
+        const uint32_t k = (uint32_t)(((oy & 1) << 1) | (ox & 1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { uint32_t kj = ((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 0xffu; if (kj != k) g[j] = 0.f; }
+      }
+      const float* ys = a.y + ((n * a.H + oy) * a.W + ox) * C + c * 8;
+      float4 y0 = *reinterpret_cast<const float4*>(ys), y1 = *reinterpret_cast<const float4*>(ys + 4);
+      const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // nn.PReLU backward (ops.cu k_prelu_bwd): gx = x > 0 ? g : w g ; gw += sum_{x <= 0} x g
+        if (!(yv[j] > 0.f)) { ps += yv[j] * g[j]; g[j] = slope * g[j]; }
+        cs[j] += g[j];
+      }
+      __half2 h0 = __floats2half2_rn(g[0] * sc, g[1] * sc), h1 = __floats2half2_rn(g[2] * sc, g[3] * sc), h2 = __floats2half2_rn(g[4] * sc, g[5] * sc), h3 = __floats2half2_rn(g[6] * sc, g[7] * sc);
+      packed.x = *reinterpret_cast<uint32_t*>(&h0); packed.y = *reinterpret_cast<uint32_t*>(&h1); packed.z = *reinterpret_cast<uint32_t*>(&h2); packed.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    dst[i] = packed;
+  }
+  if (!a.part) return;
+  // fixed-order block reduction of the nine partial sums
+  double v[9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = warp_sum_d((double)cs[j]);
+  v[8] = warp_sum_d((double)ps);
+  const int w = tid >> 5, l = tid & 31;
+  if (l == 0) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) red[j][w] = v[j];
+  }
+  __syncthreads();
+  if (tid < 9) {
+    double s = 0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[tid][q];
+    a.part[(n * Cq + c) * 9 + tid] = s;
+  }
+}
+// gb[c] += sum_n part[n][c / 8][c % 8] ; gpw += sum_{n, plane} part[n][plane][8]   (fixed order)
+__global__ void __launch_bounds__(256) k_act_bwd_final(const double* __restrict__ part, int N, int Cq, float* __restrict__ gb, float* __restrict__ gpw) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  for (int c = tid; c < Cq * 8; c += blockDim.x) {
+    double s = 0;
+    for (int n = 0; n < N; ++n) s += part[((long)n * Cq + (c >> 3)) * 9 + (c & 7)];
+    gb[c] += (float)s;
+  }
+  double s = 0;
+  for (int i = tid; i < N * Cq; i += blockDim.x) s += part[(long)i * 9 + 8];
+  s = warp_sum_d(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { double t = 0; for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q]; *gpw += (float)t; }
+}
+
+size_t act_bwd_operand_bytes(int N, int H, int W, int C, int k) {
+  const int p = (k - 1) / 2;
+  return (size_t)N * (C / 8) * (((H + 15) / 16) * 16 + 2 * p) * (W + 2 * p) * 16;
+}
+// y [N,H,W,C] with C % 64 == 0.  g[i]: upstream gradients at the pooled resolution.  part: N * C/8 * 9 doubles, or null with gb / gpw null.
+int act_bwd_pack(const float* const* g, const unsigned int* const* amax, int ng, int g_stride, int g_off, const float* mask, int mask_stride, int pool, const uint8_t* idx,
+                 const float* y, const float* pw, int N, int H, int W, int C, int k, uint8_t* gq, float* scale2, double* part, float* gb_acc, float* gpw_acc) {
+  if (C % 64 || ng < 1 || ng > 4 || (pool && ((H | W) & 1)) || ((g_stride | g_off) & 3)) return set_err(CG_ERR_ARG, "act_bwd_pack: unsupported shape");
+  ActBwdArgs a{};
+  for (int i = 0; i < ng; ++i) { a.g[i] = g[i]; a.amax[i] = amax[i]; }
+  a.ng = ng; a.g_stride = g_stride; a.g_off = g_off; a.mask = mask; a.mask_stride = mask_stride; a.pool = pool; a.idx = idx; a.y = y; a.pw = pw;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.scale2 = scale2; a.gq = gq; a.p = (k - 1) / 2; a.Hq = ((H + 15) / 16) * 16 + 2 * a.p; a.Wq = W + 2 * a.p;
+  a.part = part;
+  ctx().next_bytes = 4.0 * N * H * W * C * (1.0 + (pool ? 0.25 : 1.0) * ng) + 16.0 * N * (C / 8) * a.Hq * a.Wq;
+  CG_LAUNCH(k_act_bwd, dim3(C / 8, N), 256, 0, a);
+  if (part) CG_LAUNCH(k_act_bwd_final, 1, 256, 0, (const double*)part, N, C / 8, gb_acc, gpw_acc);
+  return CG_OK;
+}
+
+}  // namespace cg

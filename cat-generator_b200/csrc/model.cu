@@ -99,8 +99,19 @@ int model_build(cg_model* m) {
     m->b2[3] = add_layer(m, 128, 128, 7, o); m->bpw2[3] = o; o += 1;
     m->h1 = add_layer(m, 20480, 256, 1, o, 64, 1); m->hpw = o; o += 1;
     m->h2 = add_layer(m, 256, 1, 1, o);
+  } else if (m->kind == CG_V32) {   // models.lua:765-804
+    const int vc[4][2] = {{C, 128}, {128, 128}, {128, 256}, {256, 256}};
+    m->nrun = 0;
+    for (int i = 0; i < 4; ++i) {
+      m->vconv[i] = add_layer(m, vc[i][0], vc[i][1], 3, o, 1, 1, false);
+      if (i == 1 || i == 3) { m->vbn[i / 2] = o; o += 2 * vc[i][1]; m->nrun += 2 * vc[i][1]; }          // SpatialBatchNormalization after conv 2 and conv 4
+    }
+    m->vlin[0] = add_layer(m, 4096, 1024, 1, o, 16, 1, false); m->vbn[2] = o; o += 2048; m->nrun += 2048;   // View(256*4*4) -> Linear -> BatchNormalization(1024)
+    m->vlin[1] = add_layer(m, 1024, 1024, 1, o, 1, 1, false); m->vbn[3] = o; o += 2048; m->nrun += 2048;
+    m->vlin[2] = add_layer(m, 1024, 2, 1, o, 1, 1, false);
   } else return set_err(CG_ERR_ARG, "unknown model kind %d", m->kind);
   m->np = o;
+  if (m->kind == CG_D32_ST3) { CG_CUDA(cudaMalloc(&m->amax, sizeof(unsigned int) * 16)); CG_CUDA(cudaMemsetAsync(m->amax, 0, sizeof(unsigned int) * 16, ctx().stream)); }
   CG_CUDA(cudaMalloc(&m->P, sizeof(float) * o));
   CG_CUDA(cudaMalloc(&m->G, sizeof(float) * o));
   CG_CUDA(cudaMemsetAsync(m->G, 0, sizeof(float) * o, ctx().stream));
@@ -146,11 +157,17 @@ int model_build(cg_model* m) {
     for (int i = 0; i < m->nst; ++i) if (m->st[i].bn) {
       CG_TRY(fill(m->run + r, 0.f, m->st[i].Co)); CG_TRY(fill(m->run + r + m->st[i].Co, 1.f, m->st[i].Co)); r += 2 * m->st[i].Co;
     }
+    if (m->kind == CG_V32) { const int bc[4] = {128, 256, 1024, 1024}; for (int i = 0; i < 4; ++i) { CG_TRY(fill(m->run + r, 0.f, bc[i])); CG_TRY(fill(m->run + r + bc[i], 1.f, bc[i])); r += 2 * bc[i]; } }
   }
   // ---- initialisation (distribution parity only; parity tests exchange parameters as data)
   const float quarter = 0.25f;
   auto set_scalar = [&](long off, float v) -> int { return fill(m->P + off, v, 1); };
-  if (m->kind != CG_D32_ST3) {
+  if (m->kind == CG_V32) {   // weight-init 'heuristic' on the top-level modules: W ~ U(+-1/sqrt(fan_in)), zero bias; BN gamma ~ U(0,1), beta 0
+    const int bc[4] = {128, 256, 1024, 1024};
+    for (int i = 0; i < 4; ++i) CG_TRY(init_layer(m, m->vconv[i], false));
+    for (int i = 0; i < 3; ++i) CG_TRY(init_layer(m, m->vlin[i], false));
+    for (int i = 0; i < 4; ++i) { CG_TRY(init_uniform(m, m->vbn[i], bc[i], 0.f, 1.f)); CG_TRY(fill(m->P + m->vbn[i] + bc[i], 0.f, bc[i])); }
+  } else if (m->kind != CG_D32_ST3) {
     CG_TRY(init_layer(m, m->lin_layer, false)); CG_TRY(set_scalar(m->oLpw, quarter));
     for (int i = 0; i < m->nst; ++i) {
       cg_gstage& s = m->st[i];
@@ -177,10 +194,16 @@ int model_build(cg_model* m) {
   return CG_OK;
 }
 
-int model_repack(cg_model* m) {
-  if (!m->dirty) return CG_OK;
-  CG_TRY(repack_model(m->jobs_dev, m->njobs, m->repack_blocks));   // every layer's fp32 operands + fp16 weight slices, one launch
-  m->dirty = false;
+// Measured (profiles/r02 bench): the full repack was 143 us per network, twice per step on the critical path, two thirds of it the fp32
+// operands that only the CUDA-core fallback reads.  They are refreshed only when a caller may take that fallback.
+int model_repack(cg_model* m, int need32) {
+  if (m->dirty) {
+    CG_TRY(repack_model(m->jobs_dev, m->njobs, m->repack_blocks, need32 ? 3 : 2));   // one launch
+    m->dirty = false; m->dirty32 = !need32;
+  } else if (need32 && m->dirty32) {
+    CG_TRY(repack_model(m->jobs_dev, m->njobs, m->repack_blocks, 1));
+    m->dirty32 = false;
+  }
   return CG_OK;
 }
 
@@ -232,8 +255,10 @@ static bool g_stage_fused(const cg_model* g, int i, int h_in) {
   return conv_tc_cached_ok(H, H, s.Ci, s.Co, s.k);
 }
 
+struct Fp32StaleScope { bool on; explicit Fp32StaleScope(bool stale) : on(stale) { if (on) ctx().fp32_operands_stale++; } ~Fp32StaleScope() { if (on) ctx().fp32_operands_stale--; } };
 int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
-  CG_TRY(model_repack(g));
+  CG_TRY(model_repack(g, !conv_tc_all_shapes_taken(B)));
+  Fp32StaleScope stale_scope(g->dirty32);
   g->nfw = 0; g->B = B;
   long F0 = (long)g->C0 * g->s0 * g->s0;
   float* zc = FW(g, (size_t)B * g->nz); NN(zc);
@@ -302,6 +327,8 @@ int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
 int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
   if (!g->B) return set_err(CG_ERR_STATE, "G backward before forward");
   if (!g->training) return set_err(CG_ERR_STATE, "G backward needs a training-mode forward (batch-stat BN)");
+  CG_TRY(model_repack(g, !conv_tc_all_shapes_taken(g->B)));   // the engine may have been switched since the forward: the operands it reads must be fresh
+  Fp32StaleScope stale_scope(g->dirty32);
   g->nbw = 0; int B = g->B, h = 32;
   float* gcur = BW(g, (size_t)B * g->C * 1024); NN(gcur);
   CG_TRY(nchw_to_nhwc(gout_nchw, gcur, B, g->C, 1024));
@@ -380,14 +407,14 @@ static int stn_forward(cg_model* m, cg_stn* s, const float* in, int B) {
   return CG_OK;
 }
 // gout, gin: [B,S,S,ch]; gin is written (sum of the sampler branch and the localisation branch, nn.ConcatTable)
-static int stn_backward(cg_model* m, cg_stn* s, const float* gout, float* gin, int B) {
+static int stn_backward(cg_model* m, cg_stn* s, const float* gout, float* gin, int B, unsigned int* amax_out = nullptr) {
   int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
   if (s->fused) {
     float* ggrid = BW(m, (size_t)B * S * S * 2); float* gl1 = BW(m, (size_t)B * 64); NN(ggrid); NN(gl1);
     float* part = nullptr;
     if (!m->skip_param_grads) { part = BW(m, (size_t)B * stn_fused_part_floats(ch, s->nth)); NN(part); }
     StnFusedParams p; StnFusedGrads g; stn_params(m, s, &p, &g);
-    return stn_fused_backward(p, g, s->in, B, s->pool1, s->c1o, s->c2o, s->pool2, s->l1o, s->theta, s->A, gout, gin, ggrid, gl1, part, m->skip_param_grads);
+    return stn_fused_backward(p, g, s->in, B, s->pool1, s->c1o, s->c2o, s->pool2, s->l1o, s->theta, s->A, gout, gin, ggrid, gl1, part, m->skip_param_grads, amax_out);
   }
   float* ggrid = BW(m, (size_t)B * S * S * 2); NN(ggrid);
   CG_TRY(bilinear_bwd(s->in, s->grid, gout, gin, ggrid, B, S, S, ch));
@@ -481,7 +508,8 @@ static int D_forward_fused(cg_model* d, int B, const float* mk, float* sig_dev, 
 }
 
 int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float* pre_dev) {
-  CG_TRY(model_repack(d));
+  CG_TRY(model_repack(d, !conv_tc_all_shapes_taken(B)));
+  Fp32StaleScope stale_scope(d->dirty32);
   CG_TRY(ensure_masks(d, B));
   d->nfw = 0; d->B = B; int C = d->C;
   const float* mk = d->masks;
@@ -535,8 +563,82 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
 // where a PReLU weight gradient goes (nowhere when parameter gradients are skipped)
 static inline float* PG(cg_model* m, long off) { return m->skip_param_grads ? nullptr : m->G + off; }
 
+// The conv part of D's backward with every chain (dropout', pool', PReLU', bias / PReLU gradients, fp16 gradient operand) as ONE kernel
+// per convolution (fuse_d.cu act_bwd_pack) and the four branch gradients summed inside the trunk's kernel.  Entered with gcatd = the
+// gradient of the masked Concat buffer (the head's Linear layers run as before).  amax slots: 0 gcatd ; 1-4 each branch's second-conv
+// input gradient ; 5-7 the transformers' input gradients ; 8 branch 4's first-conv input gradient ; 9 trunk conv 2's input gradient.
+static int conv_layer_bwd_gq(cg_model* m, int li, const float* x, const uint8_t* xq, const uint8_t* gq, const float* sc, float* gx, int N, int H, unsigned int* amax_next) {
+  cg_layer& L = m->layers[li];
+  ctx().next_amax = gx ? amax_next : nullptr;
+  int s = conv_bwd_tc_gq(x, xq, gq, sc, L.Wd, gx, N, H, H, L.s.Ci, L.s.Co, L.s.k, m->skip_param_grads ? nullptr : m->G + L.oW);
+  ctx().next_amax = nullptr;
+  return s;
+}
+struct ActBwd { uint8_t* gq; float* sc; double* part; };
+static int act_bwd_alloc(cg_model* d, ActBwd* r, int N, int H, int C, int k) {
+  r->gq = (uint8_t*)BW(d, act_bwd_operand_bytes(N, H, H, C, k) / 4); r->sc = BW(d, 4);
+  r->part = d->skip_param_grads ? nullptr : (double*)BW(d, (size_t)N * (C / 8) * 9 * 2);
+  if (!r->gq || !r->sc || (!d->skip_param_grads && !r->part)) return set_err(CG_ERR_CUDA, "device allocation failed");
+  return CG_OK;
+}
+static int D_backward_fused(cg_model* d, const float* gcatd, float* gx_nchw) {
+  const int B = d->B, C = d->C;
+  const float* mk_trunk = d->masks; const float* mk_br = d->masks + (long)B * 64; const float* mk_head = d->masks + (long)B * (64 * 4 + 128);
+  unsigned int* am = d->amax;
+  CG_CUDA(cudaMemsetAsync(am, 0, sizeof(unsigned int) * 16, ctx().stream));
+  CG_TRY(absmax_into(gcatd, (long)B * 20480, am + 0));
+  const long nT = (long)B * 256 * 64;
+  const float* gT_part[4];
+  CG_TRY(lanes_fork());
+  for (int b = 0; b < 4; ++b) {
+    LaneScope lane(b); CG_TRY(lane.status);
+    const int Co = b < 3 ? 64 : 128, k1 = b < 3 ? 3 : 5, k2 = b < 3 ? 3 : 7;
+    // second conv of the branch: upstream = this branch's slot of the Concat gradient, head dropout mask applied on the way (models.lua:695)
+    ActBwd r2; CG_TRY(act_bwd_alloc(d, &r2, B, 8, Co, k2));
+    { const float* g[1] = {gcatd}; const unsigned int* a[1] = {am + 0};
+      CG_TRY(act_bwd_pack(g, a, 1, 320, b * 64, mk_head + b * 64, 320, 0, nullptr, d->bc2[b], d->P + d->bpw2[b], B, 8, 8, Co, k2, r2.gq, r2.sc, r2.part,
+                          d->skip_param_grads ? nullptr : d->G + d->layers[d->b2[b]].ob, PG(d, d->bpw2[b]))); }
+    float* gdr = BW(d, (size_t)B * 64 * Co); NN(gdr);
+    CG_TRY(conv_layer_bwd_gq(d, d->b2[b], nullptr, d->xq_b2[b], r2.gq, r2.sc, gdr, B, 8, am + 1 + b));
+    // first conv: SpatialDropout' -> MaxPool' -> PReLU'
+    ActBwd r1; CG_TRY(act_bwd_alloc(d, &r1, B, 16, Co, k1));
+    { const float* g[1] = {gdr}; const unsigned int* a[1] = {am + 1 + b};
+      CG_TRY(act_bwd_pack(g, a, 1, Co, 0, mk_br + (long)B * 64 * b, Co, 2, d->bidx[b], d->bc1[b], d->P + d->bpw1[b], B, 16, 16, Co, k1, r1.gq, r1.sc, r1.part,
+                          d->skip_param_grads ? nullptr : d->G + d->layers[d->b1[b]].ob, PG(d, d->bpw1[b]))); }
+    float* gbin = BW(d, nT); NN(gbin);
+    CG_TRY(conv_layer_bwd_gq(d, d->b1[b], b < 3 ? d->stn[b + 1].out : nullptr, b == 3 ? d->xq_b4 : nullptr, r1.gq, r1.sc, gbin, B, 16, b == 3 ? am + 8 : nullptr));
+    if (b < 3) {
+      float* gs = BW(d, nT); NN(gs);
+      CG_TRY(stn_backward(d, &d->stn[b + 1], gbin, gs, B, am + 5 + b));
+      gT_part[b] = gs;
+    } else gT_part[b] = gbin;
+  }
+  CG_TRY(lanes_join());
+  // trunk conv 2: the four branch gradients are summed here (nn.Concat backward), then SpatialDropout' -> AvgPool' -> PReLU'
+  ActBwd rt2; CG_TRY(act_bwd_alloc(d, &rt2, B, 32, 64, 3));
+  { const unsigned int* a[4] = {am + 5, am + 6, am + 7, am + 8};
+    CG_TRY(act_bwd_pack(gT_part, a, 4, 64, 0, mk_trunk, 64, 1, nullptr, d->tc2, d->P + d->t2pw, B, 32, 32, 64, 3, rt2.gq, rt2.sc, rt2.part,
+                        d->skip_param_grads ? nullptr : d->G + d->layers[d->t2].ob, PG(d, d->t2pw))); }
+  const long n64 = (long)B * 1024 * 64;
+  float* gta1 = BW(d, n64); NN(gta1);
+  CG_TRY(conv_layer_bwd_gq(d, d->t2, nullptr, d->xq_t2, rt2.gq, rt2.sc, gta1, B, 32, am + 9));
+  ActBwd rt1; CG_TRY(act_bwd_alloc(d, &rt1, B, 32, 64, 3));
+  { const float* g[1] = {gta1}; const unsigned int* a[1] = {am + 9};
+    CG_TRY(act_bwd_pack(g, a, 1, 64, 0, nullptr, 0, 0, nullptr, d->tc1, d->P + d->t1pw, B, 32, 32, 64, 3, rt1.gq, rt1.sc, rt1.part,
+                        d->skip_param_grads ? nullptr : d->G + d->layers[d->t1].ob, PG(d, d->t1pw))); }
+  float* gs0 = BW(d, (size_t)B * 1024 * C); NN(gs0);
+  CG_TRY(conv_layer_bwd_gq(d, d->t1, d->stn[0].out, nullptr, rt1.gq, rt1.sc, gs0, B, 32, nullptr));
+  float* gin = BW(d, (size_t)B * 1024 * C); NN(gin);
+  CG_TRY(stn_backward(d, &d->stn[0], gs0, gin, B));
+  if (gx_nchw) CG_TRY(nhwc_to_nchw(gin, gx_nchw, B, C, 1024));        // MODEL_D.modules[1].gradInput (adversarial.lua:193)
+  CG_TRY(side_wait_all());
+  return CG_OK;
+}
+
 int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   if (!d->B) return set_err(CG_ERR_STATE, "D backward before forward");
+  CG_TRY(model_repack(d, !conv_tc_all_shapes_taken(d->B)));
+  Fp32StaleScope stale_scope(d->dirty32);
   d->nbw = 0; int B = d->B, C = d->C;
   const float* mk_trunk = d->masks;
   const float* mk_br = d->masks + (long)B * 64;
@@ -547,6 +649,7 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   float* gha1 = BW(d, (size_t)B * 256); NN(gha1); CG_TRY(mask_elems(ghd, mk_fc, gha1, (long)B * 256));
   float* gh1 = BW(d, (size_t)B * 256); NN(gh1); CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, PG(d, d->hpw), (long)B * 256));
   float* gcatd = BW(d, (size_t)B * 20480); NN(gcatd); CG_TRY(layer_bwd(d, d->h1, d->catd, gh1, gcatd, B, 1, 1));
+  if (d->dfused && d->stn[0].fused && getenv("CATGEN_DBWD_UNFUSED") == nullptr) return D_backward_fused(d, gcatd, gx_nchw);
   float* gcat = BW(d, (size_t)B * 20480); NN(gcat); CG_TRY(mask_channels(gcatd, mk_head, gcat, B, 64, 320));
   long nT = (long)B * 256 * 64;
   float* gT = BW(d, nT); NN(gT); CG_TRY(fill(gT, 0.f, nT));
@@ -587,4 +690,53 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   return CG_OK;
 }
 
+}  // namespace cg
+
+namespace cg {
+// =================================================================== V (models.lua:765-804), evaluate() mode forward
+// activation = nn.LeakyReLU with no argument: negval = 1/100 (not D's 0.333)
+int V_forward_dev(cg_model* v, const float* x_nchw, int B, float* out_dev) {
+  CG_TRY(model_repack(v, 1));   // V's shapes are not in conv_tc_all_shapes_taken's list: keep the fp32 operands fresh for any layer the engine declines
+  Fp32StaleScope stale_scope(v->dirty32);
+  v->nfw = 0; v->B = B;
+  const int C = v->C;
+  float* x = FW(v, (size_t)B * 1024 * C); NN(x);
+  CG_TRY(nchw_to_nhwc(x_nchw, x, B, C, 1024));
+  const int hw[4] = {32, 16, 8, 8}, co[4] = {128, 128, 256, 256};
+  const float* cur = x; long r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const long n = (long)B * hw[i] * hw[i] * co[i];
+    float* y = FW(v, n); NN(y);
+    CG_TRY(layer_fwd(v, v->vconv[i], cur, y, B, hw[i], hw[i]));
+    if (i == 1 || i == 3) {   // SpatialBatchNormalization, running statistics
+      float* b = FW(v, n); NN(b);
+      CG_TRY(bn_fwd_eval(y, v->P + v->vbn[i / 2], v->P + v->vbn[i / 2] + co[i], b, v->run + r, v->run + r + co[i], (long)B * hw[i] * hw[i], co[i], 1e-5f));
+      r += 2 * co[i]; y = b;
+    }
+    float* a = FW(v, n); NN(a);
+    CG_TRY(lrelu_fwd(y, 0.01f, a, n));
+    cur = a;
+    if (i != 2) {             // SpatialMaxPooling(2,2) after conv 1, 2 and 4
+      float* p = FW(v, n / 4); uint8_t* idx = (uint8_t*)FW(v, n / 16 + 4); NN(p); NN(idx);
+      CG_TRY(maxpool2_fwd(a, p, idx, B, hw[i], hw[i], co[i]));
+      cur = p;
+    }
+  }
+  // nn.SpatialDropout() in evaluate(): y = (1 - p) x with p = 0.5; nn.Dropout() is the identity
+  const long nf = (long)B * 4096;
+  float* f = FW(v, nf); NN(f);
+  CG_CUDA(cudaMemcpyAsync(f, cur, sizeof(float) * nf, cudaMemcpyDeviceToDevice, ctx().stream));
+  CG_TRY(scale_inplace(f, 0.5f, nf));
+  cur = f;
+  for (int i = 0; i < 2; ++i) {
+    float* y = FW(v, (size_t)B * 1024); float* b = FW(v, (size_t)B * 1024); float* a = FW(v, (size_t)B * 1024); NN(y); NN(b); NN(a);
+    CG_TRY(layer_fwd(v, v->vlin[i], cur, y, B, 1, 1));
+    CG_TRY(bn_fwd_eval(y, v->P + v->vbn[2 + i], v->P + v->vbn[2 + i] + 1024, b, v->run + r, v->run + r + 1024, B, 1024, 1e-5f)); r += 2048;
+    CG_TRY(lrelu_fwd(b, 0.01f, a, (long)B * 1024));
+    cur = a;
+  }
+  float* logit = FW(v, (size_t)B * 2); NN(logit);
+  CG_TRY(layer_fwd(v, v->vlin[2], cur, logit, B, 1, 1));
+  return softmax_rows(logit, out_dev, B, 2);
+}
 }  // namespace cg

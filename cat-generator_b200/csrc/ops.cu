@@ -112,6 +112,17 @@ __global__ void k_sigmoid_bwd(const float* __restrict__ y, const float* __restri
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) { float v = y[i]; gx[i] = gy[i] * v * (1.f - v); }
 }
 int sigmoid_bwd(const float* y, const float* gy, float* gx, long n) { CG_LAUNCH(k_sigmoid_bwd, grid1d(n, 256, 4), 256, 0, y, gy, gx, n); return CG_OK; }
+// nn.SoftMax: y = exp(x - max) / sum exp(x - max) per row (one thread per row; rows here are 2 wide)
+__global__ void k_softmax_rows(const float* __restrict__ x, float* __restrict__ y, long rows, int C) {
+  for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < rows; r += (long)gridDim.x * blockDim.x) {
+    const float* s = x + r * C; float m = s[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, s[c]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(s[c] - m);
+    for (int c = 0; c < C; ++c) y[r * C + c] = expf(s[c] - m) / sum;
+  }
+}
+int softmax_rows(const float* x, float* y, long rows, int C) { CG_LAUNCH(k_softmax_rows, grid1d(rows, 128), 128, 0, x, y, rows, C); return CG_OK; }
 __global__ void k_add(float* __restrict__ a, const float* __restrict__ b, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) a[i] += b[i];
 }

@@ -16,6 +16,7 @@ int lrelu_fwd(const float* x, float s, float* y, long n);
 int lrelu_bwd(const float* x, const float* gy, float s, float* gx, long n);
 int sigmoid_fwd(const float* x, float* y, long n);
 int sigmoid_bwd(const float* y, const float* gy, float* gx, long n);
+int softmax_rows(const float* x, float* y, long rows, int C);   // nn.SoftMax over the last dimension
 int add_inplace(float* a, const float* b, long n);
 int fill(float* a, float v, long n);
 int mask_channels(const float* x, const float* mask_nc, float* y, int N, int HW, int C);
@@ -104,6 +105,8 @@ size_t conv_tc_operand_bytes(int N, int H, int W, int Ci, int k);
 int bn_prelu_up_pack(const float* x, const float* gamma, const float* beta, const float* mean, const float* invstd, const float* pw,
                      float* bn_out, uint8_t* xq, int N, int h, int w, int C, int up, int k);
 int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k);
+int conv_bwd_tc_gq(const float* x, const uint8_t* xq_prepacked, const uint8_t* gq, const float* scale2, const float* Wd, float* gx,
+                   int N, int H, int W, int Ci, int Co, int k, float* gW_acc);
 
 
 // ---- whole-model repack in ONE launch (conv_tc.cu): fp32 fprop/dgrad/bias operands of every layer plus, for layers the
@@ -114,7 +117,8 @@ struct PackJob {
   ConvSpec s; int need_dgrad, CBf, CBd;
   int blk0, nblk;                                                 // this job's slice of the flat grid (blocks proportional to its weight count)
 };
-int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks);
+int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks, int mode);   // mode: 1 fp32 operands, 2 bias + fp16 slices, 3 both
+bool conv_tc_all_shapes_taken(int B);   // true when every conv / Linear call at batch B goes to the tensor-core engine (no fp32 operand is read)
 bool conv_tc_wslice_plan(int Cin, int Cout, int k, int* CB, size_t* bytes);   // fp16 forward-conv slices for Cin -> Cout
 void conv_tc_register_wslices(const float* key, const uint8_t* wq, int CB);
 void conv_tc_unregister_wslices(const float* key);

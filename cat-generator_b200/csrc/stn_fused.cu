@@ -43,7 +43,11 @@ __device__ __forceinline__ void conv3x3_16(const float* __restrict__ x_s, const 
         const int xx = x + kx - 1; if (xx < 0 || xx >= P) continue;
         const float* xr = x_s + (yy * P + xx) * Ci;
         const float* wr = w_s + ((ky * 3 + kx) * Ci) * 17 + co;
-        for (int ci = 0; ci < Ci; ++ci) acc += xr[ci] * wr[ci * 17];
+        // four independent chains (a single one ran at one FMA per shared-memory latency: the kernels were latency-bound at 8 warps per SM)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f; int ci = 0;
+        for (; ci + 4 <= Ci; ci += 4) { a0 += xr[ci] * wr[ci * 17]; a1 += xr[ci + 1] * wr[(ci + 1) * 17]; a2 += xr[ci + 2] * wr[(ci + 2) * 17]; a3 += xr[ci + 3] * wr[(ci + 3) * 17]; }
+        for (; ci < Ci; ++ci) a0 += xr[ci] * wr[ci * 17];
+        acc += (a0 + a1) + (a2 + a3);
       }
     }
     out_s[p * 16 + co] = acc;
@@ -66,7 +70,7 @@ __device__ __forceinline__ void load_conv_w(const float* __restrict__ W, float* 
 
 __device__ __forceinline__ void atm_eval(const float* th, int rot, int scl, int trn, float* M6);   // ops.cu formulas, restated below
 
-__global__ void __launch_bounds__(256) k_stn_loc_fwd(StnArgs a) {
+__global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q;
   const StnSmem m = stn_smem(ch, S);
@@ -95,13 +99,21 @@ __global__ void __launch_bounds__(256) k_stn_loc_fwd(StnArgs a) {
   __syncthreads();
   {   // nn.View + nn.Linear(f, 64): Torch feature index ft = c*Q*Q + s for our [s][c].  One warp per output row, lanes over consecutive
       // ft (coalesced weight reads), fixed shuffle tree
-    const int warp = tid >> 5, lane = tid & 31, QQ = Q * Q;
-    for (int o = warp; o < 64; o += (int)(blockDim.x >> 5)) {
-      const float* Wr = a.L1 + (size_t)o * f;
-      float acc = 0.f;
-      for (int ft = lane; ft < f; ft += 32) { int c = ft / QQ, s2 = ft - c * QQ; acc += pool2[s2 * 16 + c] * Wr[ft]; }
-      acc = warp_sum(acc);
-      if (lane == 0) { float v = acc + a.lb1[o]; a.l1o[(size_t)b * 64 + o] = v; v64[o] = lrelu_f(v); }
+    // (a single dependent chain of L2 loads per warp made this loop 60 of the kernel's 85 us: four rows at a time, four loads each in flight)
+    const int warp = tid >> 5, lane = tid & 31, QQ = Q * Q, nw = (int)(blockDim.x >> 5);
+    for (int o0 = warp * 4; o0 < 64; o0 += nw * 4) {
+      const float* Wr = a.L1 + (size_t)o0 * f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ft = lane; ft < f; ft += 32) {
+        const int c = ft / QQ, s2 = ft - c * QQ; const float pv = pool2[s2 * 16 + c];
+        const float w0 = Wr[ft], w1 = Wr[(size_t)f + ft], w2 = Wr[(size_t)2 * f + ft], w3 = Wr[(size_t)3 * f + ft];
+        acc[0] += pv * w0; acc[1] += pv * w1; acc[2] += pv * w2; acc[3] += pv * w3;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float sum = warp_sum(acc[r]);
+        if (lane == 0) { const int o = o0 + r; float v = sum + a.lb1[o]; a.l1o[(size_t)b * 64 + o] = v; v64[o] = lrelu_f(v); }
+      }
     }
   }
   __syncthreads();
@@ -223,6 +235,7 @@ struct StnBwdArgs {
   float* gin;                          // [B,S,S,ch]: the sampler's input gradient; the localisation branch's is ADDED (nn.ConcatTable)
   float* gl1;                          // [B,64]  gradient w.r.t. Linear1's output (for the cross-batch weight gradient)
   float* part;                         // per-image parameter-gradient partials, Torch layout: [B][np_part] or null (parameter gradients skipped)
+  unsigned int* amax_out;              // optional: max|gin| after both branches were summed (float bits)
   int np_part;                         // = 16*ch*9 + 16 + 16*16*9 + 16 + 64 + nth*64 + nth   (W1,b1,W2,b2,lb1,L2,lb2; L1's weight goes through gl1)
 };
 __device__ __forceinline__ float block_sum_f(float v, float* scratch) {   // fixed order; result valid in every thread
@@ -245,8 +258,10 @@ __device__ __forceinline__ void conv3x3_dgrad(const float* __restrict__ gy_s, co
         const int xx = x - kx + 1; if (xx < 0 || xx >= P) continue;
         const float* g = gy_s + (yy * P + xx) * 16;
         const float* wr = w_s + ((ky * 3 + kx) * Ci + ci) * 17;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int co = 0; co < 16; ++co) acc += g[co] * wr[co];
+        for (int co = 0; co < 16; co += 4) { a0 += g[co] * wr[co]; a1 += g[co + 1] * wr[co + 1]; a2 += g[co + 2] * wr[co + 2]; a3 += g[co + 3] * wr[co + 3]; }
+        acc += (a0 + a1) + (a2 + a3);
       }
     }
     gx_s[i] = acc;
@@ -279,7 +294,7 @@ __device__ __forceinline__ void conv3x3_wgrad(const float* __restrict__ x_s, con
   for (int co = threadIdx.x; co < 16; co += blockDim.x) { float acc = 0.f; for (int p = 0; p < P * P; ++p) acc += gy_s[p * 16 + co]; gb[co] = acc; }
 }
 
-__global__ void __launch_bounds__(256) k_stn_loc_bwd(StnBwdArgs q) {
+__global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
   extern __shared__ float sm[];
   const StnArgs& a = q.f;
   const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q, nth = a.nth;
@@ -322,9 +337,13 @@ __global__ void __launch_bounds__(256) k_stn_loc_bwd(StnBwdArgs q) {
   // ---- Linear(f, 64) backward (input gradient): gpool2[s][c] = sum_o L1[o][c*Q*Q + s] * gl1[o]
   for (int ft = tid; ft < f; ft += blockDim.x) {                           // consecutive threads read consecutive weights of each row
     const int c = ft / (Q * Q), s2 = ft - c * Q * Q;
-    float acc = 0.f;
-    for (int o = 0; o < 64; ++o) acc += a.L1[(size_t)o * f + ft] * v64[o];
-    pool2[s2 * 16 + c] = acc;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                            // four independent chains: four L2 loads in flight per thread
+#pragma unroll 4
+    for (int o = 0; o < 64; o += 4) {
+      a0 += a.L1[(size_t)o * f + ft] * v64[o]; a1 += a.L1[(size_t)(o + 1) * f + ft] * v64[o + 1];
+      a2 += a.L1[(size_t)(o + 2) * f + ft] * v64[o + 2]; a3 += a.L1[(size_t)(o + 3) * f + ft] * v64[o + 3];
+    }
+    pool2[s2 * 16 + c] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   // ---- AvgPool2 backward + LeakyReLU backward: gc2 (in cs) = lrelu'(c2o) * gpool2 / 4
@@ -350,9 +369,16 @@ __global__ void __launch_bounds__(256) k_stn_loc_bwd(StnBwdArgs q) {
   conv3x3_dgrad(cs, w1, pool1, P, ch);                                      // pool1 <- gpool1 (its forward values were consumed above)
   __syncthreads();
   float* gin = q.gin + (size_t)b * S * S * ch;
+  float amx = 0.f;
   for (int i = tid; i < S * S * ch; i += blockDim.x) {
     const int c = i % ch, p = i / ch, y = p / S, x = p - y * S;
-    gin[i] += pool1[((y >> 1) * P + (x >> 1)) * ch + c] * 0.25f;
+    const float v = gin[i] + pool1[((y >> 1) * P + (x >> 1)) * ch + c] * 0.25f;
+    gin[i] = v; amx = fmaxf(amx, fabsf(v));
+  }
+  if (q.amax_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if ((tid & 31) == 0 && amx > 0.f) atomicMax(q.amax_out, __float_as_uint(amx));
   }
 }
 
@@ -368,7 +394,13 @@ __global__ void k_stn_param_reduce(StnRedArgs r) {
   for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     float acc = 0.f;
     if (e < r.np_part) {
-      for (int b = 0; b < r.B; ++b) acc += r.part[(size_t)b * r.np_part + e];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f; int b = 0;                 // fixed association, four loads in flight
+      for (; b + 4 <= r.B; b += 4) {
+        a0 += r.part[(size_t)b * r.np_part + e]; a1 += r.part[(size_t)(b + 1) * r.np_part + e];
+        a2 += r.part[(size_t)(b + 2) * r.np_part + e]; a3 += r.part[(size_t)(b + 3) * r.np_part + e];
+      }
+      for (; b < r.B; ++b) a0 += r.part[(size_t)b * r.np_part + e];
+      acc = (a0 + a1) + (a2 + a3);
       float* dst; int o = (int)e;
       if (o < ob1) dst = r.gW1 + o; else if (o < oW2) dst = r.gb1 + (o - ob1); else if (o < ob2) dst = r.gW2 + (o - oW2); else if (o < olb1) dst = r.gb2 + (o - ob2);
       else if (o < oL2) dst = r.glb1 + (o - olb1); else if (o < olb2) dst = r.gL2 + (o - oL2); else dst = r.glb2 + (o - olb2);
@@ -378,8 +410,13 @@ __global__ void k_stn_param_reduce(StnRedArgs r) {
       // the Torch feature index ft = c*Q*Q + s
       const long w = e - r.np_part; const int o = (int)(w / r.f), mine = (int)(w - (long)o * r.f);
       const int c = mine & 15, s = mine >> 4, ft = c * r.Q * r.Q + s;
-      for (int b = 0; b < r.B; ++b) acc += r.gl1[(size_t)b * 64 + o] * r.pool2[(size_t)b * r.f + mine];
-      r.gL1[(size_t)o * r.f + ft] += acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f; int b = 0;
+      for (; b + 4 <= r.B; b += 4) {
+        a0 += r.gl1[(size_t)b * 64 + o] * r.pool2[(size_t)b * r.f + mine]; a1 += r.gl1[(size_t)(b + 1) * 64 + o] * r.pool2[(size_t)(b + 1) * r.f + mine];
+        a2 += r.gl1[(size_t)(b + 2) * 64 + o] * r.pool2[(size_t)(b + 2) * r.f + mine]; a3 += r.gl1[(size_t)(b + 3) * 64 + o] * r.pool2[(size_t)(b + 3) * r.f + mine];
+      }
+      for (; b < r.B; ++b) a0 += r.gl1[(size_t)b * 64 + o] * r.pool2[(size_t)b * r.f + mine];
+      r.gL1[(size_t)o * r.f + ft] += (a0 + a1) + (a2 + a3);
     }
   }
 }
@@ -399,7 +436,7 @@ int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* po
   a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2;
   a.B = B; a.ch = p.ch; a.S = p.S; a.rot = p.rot; a.scl = p.scl; a.trn = p.trn; a.nth = p.nth; a.in = in;
   a.pool1 = pool1; a.c1o = c1o; a.c2o = c2o; a.pool2 = pool2; a.l1o = l1o; a.theta = theta; a.A = A;
-  CG_LAUNCH(k_stn_loc_fwd, B, 256, stn_smem_bytes(p.ch, p.S), a);
+  CG_LAUNCH(k_stn_loc_fwd, B, 512, stn_smem_bytes(p.ch, p.S), a);
   long npix = (long)B * p.S * p.S;
   ctx().next_bytes = 8.0 * (double)npix * p.ch;
   CG_LAUNCH(k_stn_sample_fwd, cdiv(npix * 32, 256), 256, 0, in, (const float*)A, out, npix, p.S, p.S, p.ch);
@@ -407,7 +444,7 @@ int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* po
 }
 // gout [B,S,S,ch] -> gin [B,S,S,ch] (written); parameter gradients accumulated into g* unless skip_param_grads
 int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const float* in, int B, const float* pool1, const float* c1o, const float* c2o, const float* pool2,
-                       const float* l1o, const float* theta, const float* A, const float* gout, float* gin, float* ggrid, float* gl1, float* part, int skip_param_grads) {
+                       const float* l1o, const float* theta, const float* A, const float* gout, float* gin, float* ggrid, float* gl1, float* part, int skip_param_grads, unsigned int* amax_out) {
   CG_TRY(stn_set_attr());
   long npix = (long)B * p.S * p.S;
   CG_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)npix * p.ch, ctx().stream));
@@ -419,8 +456,8 @@ int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const fl
   a.B = B; a.ch = p.ch; a.S = p.S; a.rot = p.rot; a.scl = p.scl; a.trn = p.trn; a.nth = p.nth; a.in = in;
   a.pool1 = const_cast<float*>(pool1); a.c1o = const_cast<float*>(c1o); a.c2o = const_cast<float*>(c2o); a.pool2 = const_cast<float*>(pool2);
   a.l1o = const_cast<float*>(l1o); a.theta = const_cast<float*>(theta); a.A = const_cast<float*>(A);
-  q.ggrid = ggrid; q.gin = gin; q.gl1 = gl1; q.np_part = stn_fused_part_floats(p.ch, p.nth); q.part = skip_param_grads ? nullptr : part;
-  CG_LAUNCH(k_stn_loc_bwd, B, 256, stn_smem_bytes(p.ch, p.S), q);
+  q.ggrid = ggrid; q.gin = gin; q.gl1 = gl1; q.np_part = stn_fused_part_floats(p.ch, p.nth); q.part = skip_param_grads ? nullptr : part; q.amax_out = amax_out;
+  CG_LAUNCH(k_stn_loc_bwd, B, 512, stn_smem_bytes(p.ch, p.S), q);
   if (!skip_param_grads) {
     StnRedArgs r{};
     const int Q = p.S / 4;

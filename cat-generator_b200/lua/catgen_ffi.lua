@@ -23,6 +23,7 @@ int cg_model_get_grads(cg_model* m, float* host); int cg_model_zero_grads(cg_mod
 int cg_model_set_mode(cg_model* m, int training);
 int cg_model_bn_running_len(const cg_model* m, int64_t* n); int cg_model_get_bn_running(cg_model* m, float* host); int cg_model_set_bn_running(cg_model* m, const float* host);
 int cg_G_forward(cg_model* g, const float* z, int B, float* out); int cg_G_backward(cg_model* g, const float* gout, float* gz);
+int cg_V_forward(cg_model* v, const float* x, int B, float* out);
 int cg_D_forward(cg_model* d, const float* x, int B, float* out_sig, float* out_pre); int cg_D_backward(cg_model* d, const float* gout, float* gx);
 int cg_bce(const float* p, const float* t, int n, float* loss, float* g);
 int cg_penalty_clamp(cg_model* m, float l1, float l2sign, float l2, float clampv, float* loss_add);
@@ -37,7 +38,7 @@ int cg_conv_upsample_bwd(const float* x, const float* gy, const float* W, float*
 ]]
 
 local M = {}
-M.G32UP, M.G32UPC, M.D32_ST3 = 0, 1, 2
+M.G32UP, M.G32UPC, M.D32_ST3, M.V32 = 0, 1, 2, 3
 M.lib = ffi.load(os.getenv("CATGEN_LIB") or "catgen")          -- libcatgen.so on the loader path
 -- the reference's error convention is assert/error (layers/SpatialConvolutionUpsample.lua:5-7): non-zero status raises
 function M.check(status) if status ~= 0 then error(ffi.string(M.lib.cg_last_error()), 2) end end

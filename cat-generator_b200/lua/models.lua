@@ -13,7 +13,7 @@ local cg = require("catgen_ffi")
 local models = {}
 
 local Net = torch.class('catgen.Net')            -- a torch class so that torch.save / torch.load can carry it (train.lua:127-137,260)
-local KIND_NAME = {[0] = "G32up", "G32up-c", "D32_st3"}
+local KIND_NAME = {[0] = "G32up", "G32up-c", "D32_st3", "V32"}
 local function attach(self, kind, C, nz, seed)
    cg.init()
    local h = ffi.new("cg_model*[1]")
@@ -63,6 +63,9 @@ function Net:forward(input)
    if self.kind == cg.D32_ST3 then
       self.output:resize(B, 1)
       cg.check(cg.lib.cg_D_forward(self.h, cg.ptr(input), B, cg.ptr(self.output), nil))
+   elseif self.kind == cg.V32 then              -- MODEL_V:forward in NN_UTILS.rateWithV (utils/nn_utils.lua:700): [B,2] SoftMax, evaluate() mode
+      self.output:resize(B, 2)
+      cg.check(cg.lib.cg_V_forward(self.h, cg.ptr(input), B, cg.ptr(self.output)))
    else
       self.output:resize(B, self.C, 32, 32)
       cg.check(cg.lib.cg_G_forward(self.h, cg.ptr(input), B, cg.ptr(self.output)))
@@ -106,5 +109,9 @@ function models.create_D(dimensions, cuda)                 -- models.lua:268-277
    assert(dimensions[2] == 32, "only create_D32_st3 is on the hot path")
    assert(cuda, "libcatgen has no CPU path")
    return catgen.Net(cg.D32_ST3, dimensions[1], 100, (OPT and OPT.seed or 1) + 1)
+end
+function models.create_V(dimensions)                       -- models.lua:716-721 -> create_V32; forward / evaluate() only (train.lua:119-123)
+   assert(dimensions[2] == 32, "only create_V32 is built")
+   return catgen.Net(cg.V32, dimensions[1], 100, (OPT and OPT.seed or 1) + 2):evaluate()
 end
 return models

@@ -36,7 +36,9 @@ typedef enum {
 typedef enum {
   CG_G32UP = 0,    /* models.lua:138-160 create_G_decoder_upsampling32  */
   CG_G32UPC = 1,   /* models.lua:196-228 create_G_decoder_upsampling32c (default G at 32x32) */
-  CG_D32_ST3 = 2   /* models.lua:640-711 create_D32_st3 (default D at 32x32) */
+  CG_D32_ST3 = 2,  /* models.lua:640-711 create_D32_st3 (default D at 32x32) */
+  CG_V32 = 3       /* models.lua:765-804 create_V32: the validator network train.lua loads (train.lua:119-123) and NN_UTILS.rateWithV scores with;
+                      forward only, evaluate() mode (train.lua:123) */
 } cg_model_kind;
 
 typedef struct cg_model cg_model;     /* opaque; owns device parameters, gradients, activations */
@@ -109,6 +111,10 @@ int cg_D_backward(cg_model* d, const float* gout, float* gx);
    (models.lua:651,658,667,676,684,695,699).  set_ queues `count` mask sets ([count][cg_D_mask_floats(B)]); the
    next `count` forwards of D consume them in order (parity tests replay a whole training step this way);
    otherwise masks come from a Philox stream seeded by cg_model_create's seed. */
+/* replaces MODEL_V:forward(images) in NN_UTILS.rateWithV (utils/nn_utils.lua:686-711): x [B,C,32,32] -> SoftMax outputs [B,2]; column 0 is
+   P(fake).  evaluate() mode only: BatchNormalization uses the running statistics (cg_model_set_bn_running: [mean_l, var_l] for V's four BN
+   layers, 128 + 256 + 1024 + 1024 channels), Dropout is the identity and SpatialDropout scales by 1 - p = 0.5. */
+int cg_V_forward(cg_model* v, const float* x, int B, float* out);
 int cg_D_mask_floats(int B, int64_t* n);
 int cg_D_get_masks(cg_model* d, float* host);
 int cg_D_set_masks(cg_model* d, const float* host, int B, int count);

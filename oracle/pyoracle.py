@@ -14,6 +14,7 @@ _SO = os.path.join(_HERE, "libcatgen_oracle.so")
 _SO64 = os.path.join(_HERE, "libcatgen_oracle_f64.so")   # the same source with float widened to double (catgen_oracle.h, OG_F64)
 
 G32UP, G32UPC, D32_ST3 = 0, 1, 2
+V32 = 3   # create_V32 (models.lua:765-804); restated below as a composition of the og_* operators, forward / evaluate() only
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
 
@@ -257,6 +258,112 @@ class Model:
         gx = np.empty((gout.shape[0], self.C, 32, 32), self.dt)
         self.L.og_D_backward(self.h, self._p(gout), self._p(gx))
         return gx
+
+
+V32_BN = (128, 256, 1024, 1024)
+
+
+def V32_nparams(C_img):
+    """getParameters() length of create_V32 (models.lua:765-804): 4 convs, 3 Linear, 4 BatchNormalization (gamma, beta)."""
+    n = 0
+    for ci, co in ((C_img, 128), (128, 128), (128, 256), (256, 256)):
+        n += co * ci * 9 + co
+    n += 1024 * 4096 + 1024 + 1024 * 1024 + 1024 + 2 * 1024 + 2
+    return n + 2 * sum(V32_BN)
+
+
+def V32_init(C_img, seed):
+    """weight-init 'heuristic' shape on V: W ~ U(+-1/sqrt(fan_in)) (placeholder distribution for tests: V is loaded from
+    a trained v_*.net in the reference, train.lua:119-123, never used at its initial values), bias 0, gamma ~ U(0,1), beta 0;
+    running mean ~ N(0, 0.1), running var ~ U(0.5, 1.5) so that evaluate()-mode BN is exercised with non-trivial statistics."""
+    rng = np.random.default_rng(seed)
+    parts, run = [], []
+
+    def wb(co, fan_in):
+        s = 1.0 / np.sqrt(fan_in)
+        parts.append(rng.uniform(-s, s, co * fan_in).astype(np.float32))
+        parts.append(rng.uniform(-0.05, 0.05, co).astype(np.float32))
+
+    def bn(c):
+        parts.append(rng.uniform(0.5, 1.5, c).astype(np.float32))
+        parts.append(rng.uniform(-0.1, 0.1, c).astype(np.float32))
+        run.append(rng.normal(0, 0.1, c).astype(np.float32))
+        run.append(rng.uniform(0.5, 1.5, c).astype(np.float32))
+
+    wb(128, C_img * 9); wb(128, 128 * 9); bn(128); wb(256, 128 * 9); wb(256, 256 * 9); bn(256)
+    wb(1024, 4096); bn(1024); wb(1024, 1024); bn(1024); wb(2, 1024)
+    flat = np.concatenate(parts)
+    assert flat.size == V32_nparams(C_img)
+    return flat, np.concatenate(run)
+
+
+def V_forward(flat, running, x):
+    """MODEL_V:forward(images) in evaluate() mode (train.lua:123; utils/nn_utils.lua:700), NCHW, through the oracle's
+    operators: conv-LeakyReLU(1/100)-maxpool, conv-BN-LReLU-maxpool-Dropout(id), conv-LReLU, conv-BN-LReLU-maxpool-
+    SpatialDropout(x0.5)-View, Linear-BN-LReLU-Dropout(id) x2, Linear-SoftMax (models.lua:769-799).  Returns [B,2]."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float32)
+    B, Ci = x.shape[0], x.shape[1]
+    o, r = [0], [0]
+
+    def take(n):
+        a = np.ascontiguousarray(flat[o[0]:o[0] + n], np.float32); o[0] += n
+        return a
+
+    def run(n):
+        a = np.ascontiguousarray(running[r[0]:r[0] + n], np.float32); r[0] += n
+        return a
+
+    def conv(h, co):
+        n, ci, hh, ww = h.shape
+        W, b = take(co * ci * 9), take(co)
+        y = np.empty((n, co, hh, ww), np.float32)
+        L.og_conv2d_fwd(P(h), P(W), P(b), P(y), n, ci, hh, ww, co, 3)
+        return y
+
+    def bn(h):
+        n, c = h.shape[0], h.shape[1]
+        hw = int(np.prod(h.shape[2:])) if h.ndim > 2 else 1
+        g, b, m, v = take(c), take(c), run(c), run(c)
+        y = np.empty_like(h)
+        L.og_bn_fwd_eval(P(h), P(g), P(b), P(y), P(m), P(v), n, c, hw, 1e-5)
+        return y
+
+    def lrelu(h):
+        y = np.empty_like(h)
+        L.og_leakyrelu_fwd(P(h), 0.01, P(y), h.size)
+        return y
+
+    def pool(h):
+        n, c, hh, ww = h.shape
+        y = np.empty((n, c, hh // 2, ww // 2), np.float32)
+        idx = np.empty(y.shape, np.int32)
+        L.og_maxpool2_fwd(P(h), P(y), IP(idx), n * c, hh, ww)
+        return y
+
+    def linear(h, out):
+        n, k = h.shape
+        W, b = take(out * k), take(out)
+        y = np.empty((n, out), np.float32)
+        L.og_linear_fwd(P(h), P(W), P(b), P(y), n, k, out)
+        return y
+
+    h = pool(lrelu(conv(x, 128)))
+    h = pool(lrelu(bn(conv(h, 128))))
+    h = lrelu(conv(h, 256))
+    h = pool(lrelu(bn(conv(h, 256)))) * np.float32(0.5)
+    h = np.ascontiguousarray(h.reshape(B, 4096))
+    h = lrelu(bn(linear(h, 1024)))
+    h = lrelu(bn(linear(h, 1024)))
+    h = linear(h, 2)
+    assert o[0] == flat.size and r[0] == running.size
+    e = np.exp(h - h.max(axis=1, keepdims=True))      # nn.SoftMax: shift by the row max, exp, normalise
+    return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
+
+
+def rateWithV(flat, running, images):
+    """utils/nn_utils.lua:686-711: 1 - mean(predictions[i][1]) (first neuron = P(fake))."""
+    return 1.0 - float(V_forward(flat, running, images)[:, 0].astype(np.float64).mean())
 
 
 def D_mask_floats(B):

@@ -127,6 +127,33 @@ def D_forward(flat, x, masks=None, C=3):
     return torch.sigmoid(pre), pre
 
 
+def V_forward(flat, running, x, C=3):
+    """models.lua:765-804 in evaluate() mode, written with torch.nn.functional (independent of the oracle's operators)."""
+    c, r = Cursor(flat), Cursor(running)
+    B = x.shape[0]
+
+    def bn(h, ch):
+        g, b, m, v = c.take(ch), c.take(ch), r.take(ch), r.take(ch)
+        return F.batch_norm(h, m, v, g, b, training=False, eps=1e-5)
+
+    def conv(h, ci, co):
+        W, b = c.take(co, ci, 3, 3), c.take(co)
+        return F.conv2d(h, W, b, padding=1)
+
+    h = F.max_pool2d(F.leaky_relu(conv(x, C, 128), 0.01), 2)
+    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 128, 128), 128), 0.01), 2)
+    h = F.leaky_relu(conv(h, 128, 256), 0.01)
+    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 256, 256), 256), 0.01), 2) * 0.5
+    h = h.reshape(B, 4096)
+    for _ in range(2):
+        W, b = c.take(1024, h.shape[1]), c.take(1024)
+        h = F.leaky_relu(bn(F.linear(h, W, b), 1024), 0.01)
+    W, b = c.take(2, 1024), c.take(2)
+    h = F.linear(h, W, b)
+    assert c.o == flat.numel() and r.o == running.numel()
+    return torch.softmax(h, 1)
+
+
 def bce(p, t, eps=1e-12):
     """nn.BCECriterion, SURVEY.md A.7 (eps inside the log, mean over elements)."""
     return -(t * torch.log(p + eps) + (1 - t) * torch.log(1 - p + eps)).mean()

@@ -131,3 +131,18 @@ def test_param_counts():
     assert po.Model(po.G32UPC, 1).n == 5189381
     assert po.Model(po.G32UP, 3).n == 2470406
     assert po.Model(po.D32_ST3, 3).n == 6664777
+
+
+@pytest.mark.parametrize("C", [1, 3])
+def test_V32_forward_matches_torch(C):
+    """F3: the oracle's create_V32 composition (evaluate() mode) against an independent torch.nn.functional restatement."""
+    flat, run = po.V32_init(C, seed=11)
+    assert flat.size == po.V32_nparams(C) == {1: 6285954, 3: 6288258}[C]
+    rng = np.random.default_rng(4)
+    x = rng.uniform(0, 1, (6, C, 32, 32)).astype(np.float32)
+    got = po.V_forward(flat, run, x)
+    want = tr.V_forward(torch.from_numpy(flat).double(), torch.from_numpy(run).double(), torch.from_numpy(x).double(), C).numpy()
+    assert got.shape == (6, 2)
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-6)
+    assert np.abs(got - want).max() < 2e-5
+    assert abs(po.rateWithV(flat, run, x) - (1 - want[:, 0].mean())) < 2e-5

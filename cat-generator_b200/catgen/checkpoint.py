@@ -35,3 +35,44 @@ def load(path, MODEL_G, MODEL_D):
         MODEL_G.set_params(gp); MODEL_G.set_bn_running(gr); MODEL_D.set_params(dp)
         opt = {k[4:]: z[k][()] if z[k].shape == () else z[k] for k in z.files if k.startswith("opt_")}
         return int(z["meta_epoch"]), opt
+
+
+# ---------------------------------------------------------------- Torch7 .net files (train.lua:252-261 writes, :127-137 and :119-123 read)
+def save_torch7(path, MODEL_G, MODEL_D, epoch=0, opt=None, plot_data=None, normalize_mean=None, normalize_std=None):
+    """saveAs(filename) (train.lua:252-261): `{D=, G=, opt=, plot_data=, epoch=, normalize_mean=, normalize_std=}` in Torch7's binary
+    serialisation, the networks as nn module trees shaped like models.lua's constructors with weights that are views into one flat
+    storage each (what getParameters() leaves behind).  See catgen/torch7.py for the format and its parity-unpinned status."""
+    from . import torch7, lib
+    obj = {"D": torch7.tree_D(MODEL_D.C, MODEL_D.get_params()),
+           "G": torch7.tree_G(MODEL_G.kind == lib.G32UPC, MODEL_G.C, MODEL_G.nz, MODEL_G.get_params(), MODEL_G.get_bn_running()),
+           "opt": dict(opt or {}), "plot_data": plot_data if plot_data is not None else {}, "epoch": int(epoch)}
+    if normalize_mean is not None:
+        obj["normalize_mean"] = normalize_mean
+    if normalize_std is not None:
+        obj["normalize_std"] = normalize_std
+    torch7.save(path, obj)
+
+
+def load_torch7(path, MODEL_G=None, MODEL_D=None, MODEL_V=None):
+    """torch.load of a reference checkpoint (train.lua:127-137: tmp.G / tmp.D / tmp.epoch; :119-123: tmp.V).  Each network present in
+    both the file and the arguments receives getParameters()'s vector (and the BatchNormalization running statistics); a length
+    mismatch raises ValueError before anything is loaded.  Returns the table without the networks (epoch, opt, plot_data, ...)."""
+    from . import torch7
+    tab = torch7.load(path)
+    if not isinstance(tab, dict):
+        raise ValueError("%s does not hold a table" % path)
+    todo = []
+    for key, model in (("G", MODEL_G), ("D", MODEL_D), ("V", MODEL_V)):
+        if model is None or key not in tab:
+            continue
+        flat, run = torch7.flat_parameters(tab[key]), torch7.bn_running(tab[key])
+        if flat.size != model.nparams:
+            raise ValueError("%s in %s has %d parameters, the network here has %d" % (key, path, flat.size, model.nparams))
+        if run.size != model.get_bn_running().size:
+            raise ValueError("%s in %s has %d running statistics, the network here has %d" % (key, path, run.size, model.get_bn_running().size))
+        todo.append((model, flat, run))
+    for model, flat, run in todo:
+        model.set_params(flat)
+        if run.size:
+            model.set_bn_running(run)
+    return {k: v for k, v in tab.items() if k not in ("G", "D", "V")}

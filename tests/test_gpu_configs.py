@@ -430,3 +430,36 @@ def test_V32_initial_state_is_evaluate_mode_identity_bn():
     assert np.abs(w1).max() <= 1 / np.sqrt(27) + 1e-6 and np.abs(w1).max() > 0.9 / np.sqrt(27)
     out = V.forward(np.random.default_rng(0).uniform(0, 1, (4, 3, 32, 32)).astype(np.float32))
     assert np.isfinite(out).all() and np.allclose(out.sum(1), 1, atol=1e-5)
+
+
+def test_torch7_net_round_trip_on_real_models(tmp_path):
+    """F2: saveAs / torch.load (train.lua:252-261,127-137,119-123) through the Torch7 binary format: G, D and V leave as nn module
+    trees and come back bit-identical in getParameters() order; G samples the same images afterwards."""
+    from catgen import nn_utils
+    g = models.create_G((3, 32, 32), 100, seed=5); d = models.create_D((3, 32, 32), True, seed=6)
+    run = np.random.default_rng(3).uniform(0.5, 1.5, g.get_bn_running().size).astype(np.float32)
+    g.set_bn_running(run)
+    path = str(tmp_path / "adversarial.net")
+    checkpoint.save_torch7(path, g, d, epoch=9, opt={"batchSize": 128, "scale": 32, "colorSpace": "rgb"}, normalize_mean=0.5, normalize_std=0.25)
+    g2 = models.create_G((3, 32, 32), 100, seed=50); d2 = models.create_D((3, 32, 32), True, seed=60)
+    rest = checkpoint.load_torch7(path, g2, d2)
+    assert rest["epoch"] == 9 and rest["opt"]["batchSize"] == 128 and rest["opt"]["colorSpace"] == "rgb" and rest["normalize_std"] == 0.25
+    assert np.array_equal(g2.get_params(), g.get_params()) and np.array_equal(d2.get_params(), d.get_params())
+    assert np.array_equal(g2.get_bn_running(), run)
+    z = np.random.default_rng(1).uniform(-1, 1, (16, 100)).astype(np.float32)
+    g.evaluate(); g2.evaluate()
+    assert np.array_equal(g.forward(z), g2.forward(z))
+    # a generator file does not load into the other architecture
+    gu = models.create_G((3, 32, 32), 100, seed=1, kind=lib.G32UP)
+    with pytest.raises(ValueError):
+        checkpoint.load_torch7(path, gu, None)
+    # V: train.lua:119-123 loads {V = ...} from v_3x32x32.net
+    from catgen import torch7
+    flat, vrun = po.V32_init(3, seed=8)
+    vpath = str(tmp_path / "v_3x32x32.net")
+    torch7.save(vpath, {"V": torch7.tree_V(3, flat, vrun), "epoch": 3})
+    V = models.create_V([3, 32, 32])
+    checkpoint.load_torch7(vpath, MODEL_V=V)
+    assert np.array_equal(V.get_params(), flat) and np.array_equal(V.get_bn_running(), vrun)
+    x = g.forward(z)
+    assert abs(nn_utils.rateWithV(V, x) - po.rateWithV(flat, vrun, x)) < 1e-3

@@ -86,6 +86,19 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def conv_shape_names(B):
+    """algorithmic MFLOP per launch -> layer name, for the convolutions of G32up-c + D32_st3 at batch B and B/2 (models.lua:196-228, 640-711)."""
+    layers = [("G.conv1 512->512 3x3 @8", 8, 512, 512, 3), ("G.conv2 512->256 3x3 @16", 16, 512, 256, 3), ("G.conv3 256->128 5x5 @32", 32, 256, 128, 5),
+              ("G.conv4 128->3 3x3 @32", 32, 128, 3, 3), ("D.trunk1 3->64 3x3 @32", 32, 3, 64, 3), ("D.trunk2 64->64 3x3 @32", 32, 64, 64, 3),
+              ("D.br1-3.conv1 64->64 3x3 @16", 16, 64, 64, 3), ("D.br1-3.conv2 64->64 3x3 @8", 8, 64, 64, 3), ("D.br4.conv1 64->128 5x5 @16", 16, 64, 128, 5),
+              ("D.br4.conv2 128->128 7x7 @8", 8, 128, 128, 7), ("G.linear 100->8192", 1, 100, 8192, 1), ("D.linear 20480->256", 1, 20480, 256, 1)]
+    out = {}
+    for n in (B, B // 2):
+        for name, hw, ci, co, k in layers:
+            out[round(2.0 * n * hw * hw * co * ci * k * k / 1e6)] = "%s B=%d" % (name, n)
+    return out
+
+
 def _host_inputs(B, rng, d=1, g=1, C=3):
     real = rng.uniform(0, 1, (d, B // 2, C, 32, 32)).astype(np.float32)
     zD = rng.uniform(-1, 1, (d, B // 2, 100)).astype(np.float32)
@@ -252,6 +265,8 @@ def main():
         if os.environ.get("CATGEN_SYNC_BN"):
             lib.check(L.cg_dist_set_sync_bn(1))
 
+    if os.environ.get("CATGEN_PRECISION"):      # experiments: cost of the compensated forward (cg_set_precision(1)); the default run ships mode 0
+        lib.check(L.cg_set_precision(int(os.environ["CATGEN_PRECISION"])))
     stage("creating models")
     B, Cc, nz = args.batch, 3, 100
     hB, img = B // 2, 3 * 1024
@@ -378,6 +393,16 @@ def main():
     # EVERY rank takes the SAME path through these steps -- profiling on (hence eager, never a graph capture) and one stream
     # everywhere: each step contains the gradient all-reduces, and in round 1 rank 0 ran them eagerly while ranks 1..7 captured a new
     # graph around the same collectives (SCALE_r01: 8-GPU run hung, GPU 0 busy, GPUs 1-7 idle).
+    if os.environ.get("CATGEN_BENCH_TIMELINE") and world == 1:
+        # experiments: ONE eager step with the concurrent lanes ON and an event pair around every launch -> which kernels overlap, where streams idle
+        barrier()
+        lib.check(L.cg_profile_enable(1))
+        dev_step(W, False)
+        barrier()
+        tb = C.create_string_buffer(1 << 18)
+        lib.check(L.cg_profile_timeline(tb, len(tb)))
+        lib.check(L.cg_profile_enable(0))
+        open(os.environ["CATGEN_BENCH_TIMELINE"], "w").write(tb.value.decode())
     barrier()
     lib.check(L.cg_set_concurrency(0))
     lib.check(L.cg_profile_enable(1))
@@ -390,7 +415,13 @@ def main():
     lib.check(L.cg_set_concurrency(1))
     barrier()
     if rank == 0:
-        prof = json.loads(buf.value.decode())
+        rows = json.loads(buf.value.decode())          # one row per (kernel, work per launch) = per layer shape
+        prof = {}
+        for r in rows:
+            a = prof.setdefault(r["kernel"], {"kernel": r["kernel"], "launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            for f in ("launches", "ms", "flops", "bytes"):
+                a[f] += r[f]
+        prof = list(prof.values())
         tot = sum(k["ms"] for k in prof)
         prof.sort(key=lambda k: -k["ms"])
         top = prof[0]
@@ -411,6 +442,16 @@ def main():
                          "replays the step as one CUDA graph with concurrent lanes, where a bracketed launch would also count time shared with other lanes" % kp)
         roof["top5"] = [{"kernel": k["kernel"], "share": round(k["ms"] / tot, 4), "launches_per_step": k["launches"] / kp} for k in prof[:5]]
         roof["kernels"] = [{"kernel": k["kernel"], "ms_per_step": round(k["ms"] / kp, 4), "launches_per_step": k["launches"] / kp} for k in prof[:30]]
+        # per layer shape: the tensor-core kernels by TFLOP/s against the measured cuBLAS peak, the byte-moving kernels by GB/s against the measured
+        # copy bandwidth (algorithmic bytes = what the kernel must read + write once)
+        shapes = sorted(rows, key=lambda r: -r["ms"])
+        names = conv_shape_names(B)
+        roof["by_shape"] = [{"kernel": r["kernel"], "layer": names.get(round(r["flops"] / r["launches"] / 1e6), "?"), "us_per_launch": round(1e3 * r["ms"] / r["launches"], 1),
+                             "launches_per_step": r["launches"] / kp, "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1),
+                             "frac_of_peak": round(r["flops"] / (r["ms"] * 1e-3) / 1e12 / pk["tf_sustained"], 3)} for r in shapes if r["flops"] > 0][:12]
+        roof["hbm_kernels"] = [{"kernel": r["kernel"], "us_per_launch": round(1e3 * r["ms"] / r["launches"], 1), "launches_per_step": r["launches"] / kp,
+                                "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1), "frac_of_peak": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 3)}
+                               for r in shapes if r["flops"] == 0 and r["bytes"] > 0][:12]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -436,7 +477,7 @@ def main():
                "data": "synthetic",
                "config": {"workload": "BASELINE configs[1] per GPU: G32up-c + D32_st3, RGB 3x32x32, batch %d per GPU (global %d), D_iterations=1, G_iterations=1, "
                                       "Adam, D_L2=1e-4, clamps 1/5, dropout on" % (B, B * world),
-                          "parallelism": "dp%d" % world, "global_batch": B * world,
+                          "parallelism": "dp%d" % world, "global_batch": B * world, "forward_precision_mode": int(L.cg_get_precision()),
                           "l2": "no explicit flush: one step touches >1 GB of activations (>> 126 MB L2) and every step has distinct inputs",
                           "algorithmic_gflop_per_step_per_gpu": fl / 1e9},
                "achieved_tflops_per_gpu": fl * K / (ms_max / 1e3) / 1e12,

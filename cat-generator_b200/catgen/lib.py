@@ -72,6 +72,7 @@ def load():
     L.cg_train_step_dev.argtypes = [C.c_void_p, C.POINTER(StepCfg), C.c_void_p, C.c_void_p, C.c_void_p, fp, fp]
     L.cg_train_step.argtypes = [C.c_void_p, C.POINTER(StepCfg), C.c_void_p, C.c_void_p, C.c_void_p, fp, fp, fp]
     L.cg_penalty_clamp.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+    L.cg_set_precision.argtypes = [C.c_int]
     L.cg_prelu_fwd.argtypes = [fp, C.c_float, fp, C.c_int64]
     L.cg_prelu_bwd.argtypes = [fp, fp, C.c_float, fp, fp, C.c_int64]
     L.cg_leakyrelu_fwd.argtypes = [fp, C.c_float, fp, C.c_int64]

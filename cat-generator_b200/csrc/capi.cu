@@ -54,7 +54,7 @@ static void* grow(void** p, size_t* cap, size_t bytes) {
   return *p;
 }
 void prof_begin(const char* name) {
-  Ctx::ProfRec r; r.name = name; r.flops = ctx().next_flops; r.bytes = ctx().next_bytes;
+  Ctx::ProfRec r; r.name = name; r.flops = ctx().next_flops; r.bytes = ctx().next_bytes; r.lane = ctx().lane;
   cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, ctx().stream); ctx().prof.push_back(r);
 }
 void prof_end() { cudaEventRecord(ctx().prof.back().b, ctx().stream); }
@@ -280,12 +280,13 @@ int cg_profile_enable(int on) {
 int cg_profile_report(char* out, int cap) {
   CG_REQUIRE_INIT(); CG_ARG(out && cap > 64); Ctx& c = ctx();
   CG_CUDA(cudaStreamSynchronize(c.stream));
-  struct Agg { const char* name; long n; double ms, flops, bytes; };
+  struct Agg { const char* name; long n; double ms, flops, bytes, f1, b1; };
   std::vector<Agg> ag;
   for (auto& r : c.prof) {
     float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
-    size_t i = 0; for (; i < ag.size(); ++i) if (!strcmp(ag[i].name, r.name)) break;
-    if (i == ag.size()) ag.push_back({r.name, 0, 0, 0, 0});
+    // one row per (kernel, algorithmic work per launch): launches of the same kernel on different layer shapes stay apart (per-shape TFLOP/s, GB/s)
+    size_t i = 0; for (; i < ag.size(); ++i) if (!strcmp(ag[i].name, r.name) && ag[i].f1 == r.flops && ag[i].b1 == r.bytes) break;
+    if (i == ag.size()) ag.push_back({r.name, 0, 0, 0, 0, r.flops, r.bytes});
     ag[i].n++; ag[i].ms += ms; ag[i].flops += r.flops; ag[i].bytes += r.bytes;
   }
   int o = snprintf(out, cap, "[");
@@ -294,10 +295,25 @@ int cg_profile_report(char* out, int cap) {
   snprintf(out + o, cap - o, "]");
   return CG_OK;
 }
+// one row per launch since cg_profile_enable(1): [kernel, lane (-1 = main stream), start_us, end_us] relative to the first launch.  With
+// cg_set_concurrency(1) the rows of different lanes overlap: this is the step's timeline (what runs beside what, where the streams idle).
+int cg_profile_timeline(char* out, int cap) {
+  CG_REQUIRE_INIT(); CG_ARG(out && cap > 64); Ctx& c = ctx();
+  CG_CUDA(cudaDeviceSynchronize());
+  int o = snprintf(out, cap, "[");
+  for (size_t i = 0; i < c.prof.size() && o < cap - 160; ++i) {
+    float t0 = 0, t1 = 0; cudaEventElapsedTime(&t0, c.prof[0].a, c.prof[i].a); cudaEventElapsedTime(&t1, c.prof[0].a, c.prof[i].b);
+    o += snprintf(out + o, cap - o, "%s[\"%s\",%d,%.1f,%.1f]", i ? "," : "", c.prof[i].name, c.prof[i].lane, 1e3 * t0, 1e3 * t1);
+  }
+  snprintf(out + o, cap - o, "]");
+  return CG_OK;
+}
 int cg_set_graph_mode(int on) { ctx().graph_mode = on ? 1 : 0; return CG_OK; }
 int cg_get_graph_mode(void) { return ctx().graph_mode; }
 int cg_set_conv_engine(int e) { if (e != 0 && e != 1) return set_err(CG_ERR_ARG, "engine must be 0 or 1"); ctx().conv_engine = e; return CG_OK; }
 int cg_get_conv_engine(void) { return ctx().conv_engine; }
+int cg_set_precision(int m) { if (m != 0 && m != 1) return set_err(CG_ERR_ARG, "precision must be 0 or 1"); ctx().precision = m; return CG_OK; }
+int cg_get_precision(void) { return ctx().precision; }
 int cg_set_concurrency(int on) { CG_REQUIRE_INIT(); if (ctx().lane != -1 || ctx().in_side) return set_err(CG_ERR_STATE, "cg_set_concurrency inside a lane"); cudaStreamSynchronize(ctx().stream); ctx().lanes_on = ctx().side_on = on ? 1 : 0; return CG_OK; }
 int cg_set_dead_grad_elim(int on) { ctx().dead_grad_elim = on ? 1 : 0; return CG_OK; }
 
@@ -549,7 +565,7 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   if (!eligible) { CG_TRY(train_step_core(t, c, real, zD, zG, nullptr, nullptr)); return read_losses(t, c, lossD, lossG); }
   cg_trainer::StepGraph* sg = nullptr;
   // the key holds everything the recorded launch sequence depends on besides buffer addresses (those: alloc_gen below)
-  const int mode_key = X.lanes_on * 2 + X.side_on + 4 * t->G->training + 8 * t->D->training + 16 * X.sync_bn + 32 * X.world;
+  const int mode_key = X.lanes_on * 2 + X.side_on + 4 * t->G->training + 8 * t->D->training + 16 * X.sync_bn + 32 * X.world + 4096 * X.precision;
   for (auto& e : t->graphs) if (!memcmp(&e.cfg, c, sizeof(cg_step_cfg)) && e.engine == X.conv_engine && e.elim == X.dead_grad_elim && e.lanes == mode_key) { sg = &e; break; }
   if (!sg) { t->graphs.emplace_back(); sg = &t->graphs.back(); sg->cfg = *c; sg->engine = X.conv_engine; sg->elim = X.dead_grad_elim; sg->lanes = mode_key; }
   // A graph bakes in raw device pointers (DBufs, workspaces, lane / side scratch).  Any reallocation since the capture --

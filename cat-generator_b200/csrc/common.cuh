@@ -51,9 +51,11 @@ struct Ctx {
   // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
   bool prof_on = false;
   double next_flops = 0, next_bytes = 0;
+  int precision = 0;                   // cg_set_precision: 1 = every FORWARD convolution of G and D runs with error-compensated operands (hi + lo fp16 pairs)
+  int split_fwd = 0;                   // > 0 inside a forward executor while precision == 1: conv_ps_run packs [hi, lo, hi] x [hi, hi, lo]
   int fp32_operands_stale = 0;         // > 0 inside a model executor that skipped refreshing the fp32 fallback operands: a fallback must fail loudly
   unsigned int* next_amax = nullptr;   // one-shot: the next conv / split-K reduction launch also records max|output| there (atomicMax on float bits; the caller zeroes it)
-  struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; };
+  struct ProfRec { const char* name; cudaEvent_t a, b; double flops, bytes; int lane; };
   std::vector<ProfRec> prof;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
 };

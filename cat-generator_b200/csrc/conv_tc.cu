@@ -642,6 +642,49 @@ __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restri
     reinterpret_cast<uint4*>(Wq)[i] = out;
   }
 }
+// ---- error-compensated forward operands (cg_set_precision(1)).  x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (and the same for W); the
+// convolution over the virtual channel list [hi(x) | lo(x) | hi(x)] against [hi(W) | hi(W) | lo(W)] accumulates hi*hi + lo*hi + hi*lo in the
+// fp32 TMEM accumulator: the dropped lo*lo term is 2^-22 relative.  Cg = channels per group (a multiple of 32, the slice width); the kernel
+// itself is unchanged -- it sees a convolution with 3*Cg input channels.  lo falls into fp16's subnormal range for |x| < ~0.1: its absolute
+// step there is 6e-8, far below the fp32 rounding of the products it corrects.
+__global__ void k_pack_act_split(const float* __restrict__ x, uint8_t* __restrict__ xq, long nchunks, int H, int W, int Ci, int Cg, int Cip, int p, int Hq, int Wq) {
+  const int Cq = Cip / 8, Gq = Cg / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
+    int xx = (int)(i % Wq); long t = i / Wq; int yy = (int)(t % Hq); t /= Hq; int c = (int)(t % Cq); long n = t / Cq;
+    int iy = yy - p, ix = xx - p;
+    const int g = c / Gq, cc = (c % Gq) * 8;        // group 0 / 2: hi, group 1: lo; planes past the third group are padding
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (g < 3 && iy >= 0 && iy < H && ix >= 0 && ix < W && cc < Ci) {
+      const float* s = x + ((n * H + iy) * W + ix) * Ci + cc;
+      uint32_t* o = &out.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = cc + 2 * j < Ci ? s[2 * j] : 0.f, b = cc + 2 * j + 1 < Ci ? s[2 * j + 1] : 0.f;
+        __half2 h = __floats2half2_rn(a, b);
+        if (g == 1) h = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
+        o[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    reinterpret_cast<uint4*>(xq)[i] = out;
+  }
+}
+// Wp[(tap,ci)][co] fp32 -> 32-channel slices over the virtual channels [hi | hi | lo], each group ncb0 blocks wide
+__global__ void k_pack_wslices32_split(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int Cop, int kk, int ncb0) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nchunks; i += (long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cop); long t = i / Cop; int c = (int)(t % 4); t /= 4; int tap = (int)(t % kk); int cbv = (int)(t / kk);
+    const int g = cbv / ncb0, ci0 = (cbv % ncb0) * 32 + c * 8;
+    uint4 out; uint32_t* o = &out.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = (co < Co && ci0 + 2 * j < Ci) ? Wp[((long)tap * Ci + ci0 + 2 * j) * Co + co] : 0.f;
+      float b = (co < Co && ci0 + 2 * j + 1 < Ci) ? Wp[((long)tap * Ci + ci0 + 2 * j + 1) * Co + co] : 0.f;
+      __half2 h = __floats2half2_rn(a, b);
+      if (g == 2) h = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(Wq)[i] = out;
+  }
+}
 // ---- CTA-pair (cta_group::2) helpers; mechanics established by tools/tc_pair_probe.cu on B200 (profiles/r02_pair_probe.txt)
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -972,9 +1015,13 @@ static bool conv_v1() { static const bool v = getenv("CATGEN_CONV_V1") != nullpt
 
 static bool linear_shape_ok(int B);
 // Zmax > 1: the caller allows a K split (nn.Linear: k = 1, at most four tiles); the partial sums go through workspace #1.
-bool conv_tc_all_shapes_taken(int B) { return ctx().conv_engine == 1 && !conv_v1() && getenv("CATGEN_DGRAD_TF32") == nullptr && linear_shape_ok(B); }
+bool conv_tc_all_shapes_taken(int B) { return ctx().conv_engine == 1 && ctx().precision == 0 && !conv_v1() && getenv("CATGEN_DGRAD_TF32") == nullptr && linear_shape_ok(B); }
 static int conv_ps_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2,
                        const uint8_t* xq_prepacked, int Zmax = 1) {
+  // compensated operands (cg_set_precision(1), forward executors only): the same kernel over 3 * Cg virtual channels
+  const bool split = ctx().split_fwd > 0 && !xq_prepacked && !scale2 && Zmax == 1;
+  const int Cir_real = Cir, Cg = ((Cir + 31) / 32) * 32;
+  if (split) Cir = 3 * Cg;
   const int Ci = ((Cir + 63) / 64) * 64, Co = ((Cor + 15) / 16) * 16;       // operand padding of the packed activations (shared with the weight gradient)
   const int p = (k - 1) / 2, kk = k * k;
   const int Hq = ((H + 15) / 16) * 16 + 2 * p, Wq = W + 2 * p, Hp = 16 + 2 * p, Wpx = 8 + 2 * p;
@@ -992,17 +1039,25 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   const int ntiles = N * (W / 8) * ((H + 15) / 16);
   size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, wq_bytes = (size_t)kk * ncb * 32 * Co * 2;
   const uint8_t* wq_cached = nullptr;
-  { auto it = wslice_registry().find(Wp); if (it != wslice_registry().end() && it->second.CB == 32) wq_cached = it->second.wq; }
+  if (!split) { auto it = wslice_registry().find(Wp); if (it != wslice_registry().end() && it->second.CB == 32) wq_cached = it->second.wq; }
   uint8_t* ws = (uint8_t*)workspace3((xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255)) + (wq_cached ? 0 : wq_bytes) + 512);
   if (!ws) return CG_ERR_CUDA;
   const uint8_t* xq = xq_prepacked ? xq_prepacked : ws;
   const uint8_t* wq = wq_cached;
   long nx = (long)(xq_bytes / 16), nw = (long)(wq_bytes / 16);
+  if (split) {
+    ctx().next_bytes = 4.0 * N * H * W * Cir_real + (double)xq_bytes;
+    CG_LAUNCH(k_pack_act_split, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir_real, Cg, Ci, p, Hq, Wq);
+    uint8_t* wqb = ws + ((xq_bytes + 255) & ~(size_t)255);
+    CG_LAUNCH(k_pack_wslices32_split, grid1d(nw, 256), 256, 0, Wp, wqb, nw, Cir_real, Cor, Co, kk, Cg / 32);
+    wq = wqb;
+  } else {
   if (!xq_prepacked) { ctx().next_bytes = 4.0 * N * H * W * Cir + (double)xq_bytes; CG_LAUNCH(k_pack_act<2>, grid1d(nx, 256), 256, 0, x, ws, nx, H, W, Cir, Ci, p, Hq, Wq, scale2); }
   if (!wq_cached) {
     uint8_t* wqb = ws + (xq_prepacked ? 0 : ((xq_bytes + 255) & ~(size_t)255));
     CG_LAUNCH(k_pack_wslices32, grid1d(nw, 256), 256, 0, Wp, wqb, nw, Cir, Cor, Co, kk);
     wq = wqb;
+  }
   }
   PsParams P{};
   P.xq = xq; P.wq = wq; P.bias = bias; P.scale2 = scale2; P.y = y; P.inv_host = 1.f;
@@ -1043,7 +1098,7 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   if (gx > ntiles) gx = ntiles;
   if (Z > 1) gx = Z;
   dim3 grid(gx, gy);
-  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * Cir;             // algorithmic (unpadded) work
+  ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * (split ? Cir_real : Cir);             // algorithmic (unpadded) work; the compensation MMAs are overhead, not work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx, tmw;
   CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
@@ -1096,6 +1151,7 @@ template <int ES>
 static int conv_tc_run(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Cir, int Cor, int k, const float* scale2 = nullptr,
                        const uint8_t* xq_prepacked = nullptr) {   // xq_prepacked: the operand already in blocked/padded form (shared gradient operand)
   if (ES == 2 && !conv_v1()) { int s4 = conv_ps_run(x, Wp, bias, y, N, H, W, Cir, Cor, k, scale2, xq_prepacked); if (s4 != CG_ERR_UNSUPPORTED) return s4; }
+  if (ctx().split_fwd > 0 && !scale2 && !xq_prepacked) return CG_ERR_UNSUPPORTED;   // compensated mode: what the round-2 kernel declines goes to the fp32 kernel, never to single fp16
   constexpr int PER = 16 / ES, KB = 128 / ES;
   const int Ci = ((Cir + KB - 1) / KB) * KB, Co = ((Cor + 15) / 16) * 16;   // padded sizes the kernel iterates over
   const int p = (k - 1) / 2, kk = k * k;
@@ -1236,6 +1292,7 @@ int conv_fwd_tc_packed(const uint8_t* xq, const float* Wp, const float* bias, fl
 
 int conv_fwd_tc(const float* x, const float* Wp, const float* bias, float* y, int N, int H, int W, int Ci, int Co, int k) {
   static const bool dgrad_tf32 = getenv("CATGEN_DGRAD_TF32") != nullptr;
+  if (k == 1 && H == 1 && W == 1 && ctx().split_fwd > 0 && !g_tc_grad_operands) return CG_ERR_UNSUPPORTED;   // compensated mode: nn.Linear forwards run on the fp32 kernel
   if (k == 1 && H == 1 && W == 1 && !conv_v1() && !dgrad_tf32 && linear_shape_ok(N) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {   // nn.Linear
     if (!g_tc_grad_operands) return linear_tc_run(x, Wp, bias, y, N, Ci, Co, nullptr, nullptr);
     const int Nimg = N <= 128 ? 1 : N / 128, Hh = N <= 128 ? N / 8 : 16;

@@ -250,13 +250,16 @@ static int layer_bwd(cg_model* m, int li, const float* x, const float* gy, float
 // A stage whose input can be produced straight into the tensor-core operand: PReLU(BN(.)) -> upsample -> fp16 pack in one pass
 // (conv_tc.cu: bn_prelu_up_pack); forward and weight gradient then share that buffer and no fp32 copy of the input exists.
 static bool g_stage_fused(const cg_model* g, int i, int h_in) {
-  if (i >= g->nst || ctx().conv_engine != 1 || !g->training) return false;
+  if (i >= g->nst || ctx().conv_engine != 1 || !g->training || ctx().precision) return false;   // compensated operands are packed by the conv call itself
   const cg_gstage& s = g->st[i]; int H = s.up ? 2 * h_in : h_in;
   return conv_tc_cached_ok(H, H, s.Ci, s.Co, s.k);
 }
 
+// cg_set_precision(1): forward executors run their convolutions with compensated operands (conv_tc.cu, k_pack_act_split)
+struct SplitScope { bool on; SplitScope() : on(ctx().precision == 1 && ctx().conv_engine == 1) { if (on) ctx().split_fwd++; } ~SplitScope() { if (on) ctx().split_fwd--; } };
 struct Fp32StaleScope { bool on; explicit Fp32StaleScope(bool stale) : on(stale) { if (on) ctx().fp32_operands_stale++; } ~Fp32StaleScope() { if (on) ctx().fp32_operands_stale--; } };
 int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
+  SplitScope split_scope;
   CG_TRY(model_repack(g, !conv_tc_all_shapes_taken(B)));
   Fp32StaleScope stale_scope(g->dirty32);
   g->nfw = 0; g->B = B;
@@ -507,7 +510,17 @@ static int D_forward_fused(cg_model* d, int B, const float* mk, float* sig_dev, 
   return CG_OK;
 }
 
+// Diagnosis knob (tests/test_gpu_configs.py reads its effect): CATGEN_D_FWD_FP32=1 runs D's FORWARD on the fp32 CUDA-core engine while the
+// backward stays on the tensor-core engine -- separates the forward's fp16 operand rounding from the backward's in the gradient error.
+struct EngineScope {
+  int saved; bool on;
+  explicit EngineScope(bool on_) : saved(ctx().conv_engine), on(on_) { if (on) ctx().conv_engine = 0; }
+  ~EngineScope() { if (on) ctx().conv_engine = saved; }
+};
 int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float* pre_dev) {
+  static const bool fwd_fp32 = getenv("CATGEN_D_FWD_FP32") != nullptr;
+  EngineScope engine_scope(fwd_fp32 && ctx().conv_engine == 1);
+  SplitScope split_scope;
   CG_TRY(model_repack(d, !conv_tc_all_shapes_taken(B)));
   Fp32StaleScope stale_scope(d->dirty32);
   CG_TRY(ensure_masks(d, B));
@@ -517,7 +530,7 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
   CG_TRY(nchw_to_nhwc(x_nchw, d->xin, B, C, 1024));                      // nn.Copy + the STN's nn.Transpose (models.lua:643,870)
   CG_TRY(stn_forward(d, &d->stn[0], d->xin, B));
   long n64 = (long)B * 1024 * 64;
-  d->dfused = ctx().conv_engine == 1 && getenv("CATGEN_D_UNFUSED") == nullptr && conv_tc_cached_ok(32, 32, 64, 64, 3);
+  d->dfused = ctx().conv_engine == 1 && ctx().precision == 0 && getenv("CATGEN_D_UNFUSED") == nullptr && conv_tc_cached_ok(32, 32, 64, 64, 3);
   if (d->dfused) return D_forward_fused(d, B, mk, sig_dev, pre_dev);
   d->tc1 = FW(d, n64); d->ta1 = FW(d, n64); d->tc2 = FW(d, n64); d->ta2 = FW(d, n64); NN(d->tc1); NN(d->ta1); NN(d->tc2); NN(d->ta2);
   CG_TRY(layer_fwd(d, d->t1, d->stn[0].out, d->tc1, B, 32, 32)); CG_TRY(prelu_fwd(d->tc1, d->P + d->t1pw, d->ta1, n64));
@@ -696,6 +709,7 @@ namespace cg {
 // =================================================================== V (models.lua:765-804), evaluate() mode forward
 // activation = nn.LeakyReLU with no argument: negval = 1/100 (not D's 0.333)
 int V_forward_dev(cg_model* v, const float* x_nchw, int B, float* out_dev) {
+  SplitScope split_scope;
   CG_TRY(model_repack(v, 1));   // V's shapes are not in conv_tc_all_shapes_taken's list: keep the fp32 operands fresh for any layer the engine declines
   Fp32StaleScope stale_scope(v->dirty32);
   v->nfw = 0; v->B = B;

@@ -14,7 +14,7 @@ typedef struct cg_model cg_model;
 typedef struct cg_trainer cg_trainer;
 typedef struct { int B, d_iters, g_iters; float D_L1, D_L2, G_L1, G_L2, D_clamp, G_clamp, lr, beta1, beta2, eps; } cg_step_cfg;
 int cg_init(int device); void cg_shutdown(void); const char* cg_last_error(void); const char* cg_version(void); int cg_sync(void);
-int cg_set_conv_engine(int engine); int cg_get_conv_engine(void);
+int cg_set_conv_engine(int engine); int cg_get_conv_engine(void); int cg_set_precision(int mode); int cg_get_precision(void);
 int cg_set_dead_grad_elim(int on); int cg_set_concurrency(int on);
 int cg_model_create(cg_model** out, int kind, int C, int nz, uint64_t seed); int cg_model_free(cg_model* m);
 int cg_model_nparams(const cg_model* m, int64_t* n);

@@ -60,6 +60,8 @@ int         cg_timer_stop(float* ms);
 /* per-launch event timing of every kernel + its algorithmic flops/bytes; report is a JSON array written to out */
 int         cg_profile_enable(int on);
 int         cg_profile_report(char* out, int cap);
+/* JSON array, one row per launch since cg_profile_enable(1): ["kernel", lane, start_us, end_us] (lane -1 = the main stream) */
+int         cg_profile_timeline(char* out, int cap);
 /* 1 (default): cg_train_step* replay the step as a CUDA graph once a configuration has run twice eagerly; 0: always eager.
    Results are the same either way (Adam's step count and the dropout RNG offset live in device memory). */
 int         cg_set_graph_mode(int on);
@@ -67,6 +69,13 @@ int         cg_get_graph_mode(void);
 /* conv engine for shapes the tensor-core path supports: 0 = fp32 CUDA-core fallback only, 1 = tcgen05 (default) */
 int         cg_set_conv_engine(int engine);
 int         cg_get_conv_engine(void);
+/* Forward operand precision of the tensor-core engine.  0 (default): activations and weights are rounded to fp16 (fp32 accumulate); generated
+   pixels stay within 1e-3 of the fp32 oracle, but rounding moves PReLU / max-pool decisions and the gradients carry ~1e-2 relative noise
+   (profiles/r01_grad_diag.txt).  1: every forward convolution of G and D splits both operands into hi + lo fp16 halves and accumulates
+   hi*hi + lo*hi + hi*lo on the tensor cores (3x the forward MMA work, ~2^-21 relative operand error); nn.Linear layers and the fused
+   forward producers fall back to fp32 / unfused kernels.  Backward passes are unchanged (scaled fp16 gradients, already ~5e-4). */
+int         cg_set_precision(int mode);
+int         cg_get_precision(void);
 /* cg_train_step*: inside fevalG the reference's MODEL_D:backward (adversarial.lua:193) also accumulates D's parameter gradients,
    which the next fevalD zeroes unread (adversarial.lua:78).  1 (default): that dead accumulation is skipped -- parameters,
    optimiser state, losses and d_out are bit-identical either way; 0: keep it, so D's gradient vector after a step holds

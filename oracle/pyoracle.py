@@ -275,7 +275,8 @@ def V32_nparams(C_img):
 def V32_init(C_img, seed):
     """weight-init 'heuristic' shape on V: W ~ U(+-1/sqrt(fan_in)) (placeholder distribution for tests: V is loaded from
     a trained v_*.net in the reference, train.lua:119-123, never used at its initial values), bias 0, gamma ~ U(0,1), beta 0;
-    running mean ~ N(0, 0.1), running var ~ U(0.5, 1.5) so that evaluate()-mode BN is exercised with non-trivial statistics."""
+    running mean ~ N(0, 0.02), running var ~ U(0.04, 0.12) so that evaluate()-mode BN is exercised with non-trivial statistics and the
+    outputs differ visibly between images."""
     rng = np.random.default_rng(seed)
     parts, run = [], []
 
@@ -287,8 +288,8 @@ def V32_init(C_img, seed):
     def bn(c):
         parts.append(rng.uniform(0.5, 1.5, c).astype(np.float32))
         parts.append(rng.uniform(-0.1, 0.1, c).astype(np.float32))
-        run.append(rng.normal(0, 0.1, c).astype(np.float32))
-        run.append(rng.uniform(0.5, 1.5, c).astype(np.float32))
+        run.append(rng.normal(0, 0.02, c).astype(np.float32))
+        run.append(rng.uniform(0.04, 0.12, c).astype(np.float32))   # about the variance the layer's input really has at these weights: keeps the signal alive through seven layers
 
     wb(128, C_img * 9); wb(128, 128 * 9); bn(128); wb(256, 128 * 9); wb(256, 256 * 9); bn(256)
     wb(1024, 4096); bn(1024); wb(1024, 1024); bn(1024); wb(2, 1024)

@@ -397,7 +397,7 @@ def tree_G(kind_c, C, nz, params, running):
 
 def _tree_stn(fl, rot, scl, trn, size, ch):
     """createSpatialTransformer (models.lua:813-905), cuda=true wiring."""
-    lrelu = lambda: _mod("nn.LeakyReLU", negval=0.01, inplace=False)
+    lrelu = lambda: _mod("nn.LeakyReLU", negative_scale=0.333, negative=_empty())   # LeakyReLU.lua:5-10
     pool = lambda: _mod("nn.SpatialAveragePooling", kW=2, kH=2, dW=2, dH=2, padW=0, padH=0, ceil_mode=False, count_include_pad=True, divide=True)
     copy = lambda a, b: _mod("nn.Copy", intype=a, outtype=b, dontCast=True)
     s4 = size // 4
@@ -443,7 +443,7 @@ def tree_V(C, params, running):
         m, v = running[r[0]:r[0] + c], running[r[0] + c:r[0] + 2 * c]; r[0] += 2 * c
         return m, v
 
-    lrelu = lambda: _mod("nn.LeakyReLU", negval=0.01, inplace=False)
+    lrelu = lambda: _mod("nn.LeakyReLU", negative_scale=0.333, negative=_empty())   # LeakyReLU.lua:5-10
     mpool = lambda: _mod("nn.SpatialMaxPooling", kW=2, kH=2, dW=2, dH=2, padW=0, padH=0, ceil_mode=False)
     drop = lambda: _mod("nn.Dropout", p=0.5, v2=True, inplace=False, noise=_empty())
     mods = [_conv(fl, "nn.SpatialConvolution", C, 128, 3), lrelu(), mpool(),

@@ -226,7 +226,7 @@ int cg_init(int device) {
   CG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   { const char* e = getenv("CATGEN_LANES"); c.lanes_on = !(e && e[0] == '0'); }
   { const char* e = getenv("CATGEN_SIDE"); c.side_on = !(e && e[0] == '0'); }
-  c.device = device; c.inited = true; c.launches = 0;
+  c.device = device; c.inited = true; c.launches = 0; c.trace_launches = getenv("CATGEN_LAUNCH_TRACE") != nullptr;
   // the page-locked scratch the loss read-back uses: allocated here, not on the first cg_train_step that asks for a loss (cudaMallocHost took
   // 1-35 ms there -- profiles/r02_bench_hiccup.txt -- and fell inside whatever region that step belonged to)
   if (!pinned(4096)) return set_err(CG_ERR_CUDA, "cudaMallocHost failed");
@@ -587,7 +587,9 @@ static int train_step_run(cg_trainer* t, const cg_step_cfg* c, const float* real
   // The graph is captured from -- and therefore always replayed from -- a state in which both networks' packed operands are fresh:
   // whatever ran since the last update (an eager forward, cg_model_set_params, a replay that ended with an Adam step) is settled by an
   // eager repack here; the host-side flags are put back to what an eager step leaves behind after every replay (sg->end_dirty_*).
-  { const int need32 = !(conv_tc_all_shapes_taken(c->B) && conv_tc_all_shapes_taken(c->B / 2)); CG_TRY(model_repack(t->G, need32)); CG_TRY(model_repack(t->D, need32)); }
+  // (G runs at batch B/2 and B inside a step, D only at B: asking D for fp32 fallback operands because of G's half batch cost one k_repack_model
+  //  launch per replay at small batches -- tools/launch_diff.py)
+  { const int need32_D = !conv_tc_all_shapes_taken(c->B), need32_G = need32_D || !conv_tc_all_shapes_taken(c->B / 2); CG_TRY(model_repack(t->G, need32_G)); CG_TRY(model_repack(t->D, need32_D)); }
   CG_CUDA(cudaMemcpyAsync(g0, real, sizeof(float) * nr, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr, zD, sizeof(float) * nzd, cudaMemcpyDeviceToDevice, X.stream));
   CG_CUDA(cudaMemcpyAsync(g0 + nr + nzd, zG, sizeof(float) * nzg, cudaMemcpyDeviceToDevice, X.stream));

@@ -51,6 +51,7 @@ struct Ctx {
   // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
   bool prof_on = false;
   double next_flops = 0, next_bytes = 0;
+  int trace_launches = 0;              // CATGEN_LAUNCH_TRACE=1: every counted launch is named on stderr (diagnosis of launch-count differences)
   int precision = 0;                   // cg_set_precision: 1 = every FORWARD convolution of G and D runs with error-compensated operands (hi + lo fp16 pairs)
   int split_fwd = 0;                   // > 0 inside a forward executor while precision == 1: conv_ps_run packs [hi, lo, hi] x [hi, hi, lo]
   int fp32_operands_stale = 0;         // > 0 inside a model executor that skipped refreshing the fp32 fallback operands: a fallback must fail loudly
@@ -97,6 +98,7 @@ int side_wait_all();              // main stream: every side stream's pending wo
     if (cg::ctx().prof_on) cg::prof_end();                                                    \
     cg::ctx().next_flops = 0; cg::ctx().next_bytes = 0;                                       \
     cg::ctx().launches++;                                                                     \
+    if (cg::ctx().trace_launches) fprintf(stderr, "[launch] %s\n", #kernel);                   \
     cudaError_t _e = cudaPeekAtLastError();                                                   \
     if (_e != cudaSuccess)                                                                    \
       return cg::set_err(CG_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_e)); \

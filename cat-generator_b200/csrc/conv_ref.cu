@@ -43,8 +43,33 @@ __global__ void k_unpack_wgrad(const float* __restrict__ gWp, float* __restrict_
     gW[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)] += gWp[i];   // accGradParameters adds
   }
 }
+// nn.Linear beside an nn.View (k = 1): gW[fo][fi] += gWp[cip][cop] with both axes permuted (torch_index).  A 32 x 32 tile through shared
+// memory: rows = the packed input features that are 32 CONSECUTIVE Torch features (so every output row is written as one 128-byte run),
+// columns = 32 consecutive packed outputs (read as 128-byte runs).  The element-per-thread kernel above wrote with a stride of Ci floats
+// (D's Linear 20480 -> 256: 114 us for 21 MB, profiles/r02_timeline.txt).
+__global__ void __launch_bounds__(256) k_unpack_linear_view(const float* __restrict__ gWp, float* __restrict__ gW, ConvSpec s) {
+  __shared__ float t[32][33];
+  const int Civ = s.Ci / s.in_hw, Cov = s.Co / s.out_hw;
+  const int fi0 = blockIdx.x * 32, cop0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int fi = fi0 + r, cop = cop0 + tx;
+    float v = 0.f;
+    if (fi < s.Ci && cop < s.Co) { const int cip = (fi % s.in_hw) * Civ + fi / s.in_hw; v = gWp[(long)cip * s.Co + cop]; }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const int cop = cop0 + c, fi = fi0 + tx;
+    if (cop < s.Co && fi < s.Ci) { const int fo = (cop % Cov) * s.out_hw + cop / Cov; gW[(long)fo * s.Ci + fi] += t[tx][c]; }
+  }
+}
 int unpack_wgrad_acc(const float* gWp, float* gW_acc, const ConvSpec& s) {
-  long n = (long)s.k * s.k * s.Ci * s.Co; CG_LAUNCH(k_unpack_wgrad, grid1d(n, 256), 256, 0, gWp, gW_acc, n, s); return CG_OK;
+  long n = (long)s.k * s.k * s.Ci * s.Co;
+  if (s.k == 1 && !(s.in_hw == 1 && s.out_hw == 1)) {
+    ctx().next_bytes = 12.0 * (double)n;
+    CG_LAUNCH(k_unpack_linear_view, dim3(cdiv(s.Ci, 32), cdiv(s.Co, 32)), 256, 0, gWp, gW_acc, s); return CG_OK;
+  }
+  CG_LAUNCH(k_unpack_wgrad, grid1d(n, 256), 256, 0, gWp, gW_acc, n, s); return CG_OK;
 }
 
 // ------------------------------------------------------------------ split-K reduction (fixed order)

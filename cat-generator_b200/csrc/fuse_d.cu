@@ -251,4 +251,71 @@ int act_bwd_pack(const float* const* g, const unsigned int* const* amax, int ng,
   return CG_OK;
 }
 
+
+// =================================================================== the discriminator's head (models.lua:697-701)
+//   Linear(20480,256) output h1o -> PReLU -> Dropout(mask) -> Linear(256,1) -> Sigmoid           (forward, one warp per sample)
+//   and its mirror image                                                                          (backward, one block)
+// As separate modules this was 6 launches forward and 13 backward on the step's main stream, each a few microseconds of dependent launch
+// latency for 32k elements (profiles/r02_timeline.txt, 1978-2513 us).  Everything here is fp32; sums run in a fixed order.
+__global__ void k_d_head_fwd(const float* __restrict__ h1o, const float* __restrict__ pw, const float* __restrict__ mask, const float* __restrict__ W2,
+                             const float* __restrict__ b2, float* __restrict__ hd, float* __restrict__ h2o, float* __restrict__ hsig, int B) {
+  const int w = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= B) return;
+  const float a = *pw; float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int o = lane + 32 * j; const long i = (long)w * 256 + o;
+    const float v = h1o[i], act = v > 0.f ? v : a * v, d = act * mask[i];
+    hd[i] = d; s = fmaf(d, W2[o], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) { const float pre = s + b2[0]; h2o[w] = pre; hsig[w] = 1.f / (1.f + expf(-pre)); }
+}
+int d_head_fwd(const float* h1o, const float* pw, const float* mask, const float* W2, const float* b2, float* hd, float* h2o, float* hsig, int B) {
+  ctx().next_bytes = 4.0 * B * 256 * 3;
+  CG_LAUNCH(k_d_head_fwd, cdiv((long)B * 32, 256), 256, 0, h1o, pw, mask, W2, b2, hd, h2o, hsig, B); return CG_OK;
+}
+// gout [B] = dLoss/dSigmoid.  Writes gh1 [B,256] (gradient w.r.t. Linear1's output); with param_grads also accumulates Linear2's weight and
+// bias gradient and the PReLU slope gradient.  1024 threads = 256 columns x 4 batch quarters, quarters combined in order 0..3.
+__global__ void __launch_bounds__(1024) k_d_head_bwd(const float* __restrict__ gout, const float* __restrict__ hsig, const float* __restrict__ hd, const float* __restrict__ h1o,
+                                                     const float* __restrict__ pw, const float* __restrict__ mask, const float* __restrict__ W2, float* __restrict__ gh1,
+                                                     float* __restrict__ gW2, float* __restrict__ gb2, float* __restrict__ gpw, int B, int param_grads) {
+  __shared__ float s_g2[1024];
+  __shared__ float red[4][256];
+  __shared__ double redd[32];
+  const int tid = threadIdx.x, o = tid & 255, bq = tid >> 8;
+  for (int b = tid; b < B; b += 1024) { const float y = hsig[b]; s_g2[b] = gout[b] * y * (1.f - y); }     // nn.Sigmoid backward
+  __syncthreads();
+  const float a = *pw, w2 = W2[o];
+  float cW2 = 0.f; double cpw = 0.0;
+  for (int b = bq; b < B; b += 4) {
+    const float g2 = s_g2[b]; const long i = (long)b * 256 + o;
+    cW2 = fmaf(g2, hd[i], cW2);                                          // Linear2: gW2[o] += gh2[b] * hd[b][o]
+    const float g = g2 * w2 * mask[i];                                    // Linear2 input gradient, Dropout backward
+    const float x = h1o[i];
+    float r;
+    if (x > 0.f) r = g; else { r = a * g; cpw += (double)(x * g); }       // PReLU backward (ops.cu k_prelu_bwd)
+    gh1[i] = r;
+  }
+  if (!param_grads) return;
+  red[bq][o] = cW2;
+  __syncthreads();
+  if (bq == 0) gW2[o] += (red[0][o] + red[1][o]) + (red[2][o] + red[3][o]);
+  // PReLU slope gradient: warp sums, then warps in order
+  cpw = warp_sum_d(cpw);
+  if ((tid & 31) == 0) redd[tid >> 5] = cpw;
+  __syncthreads();
+  if (tid == 0) { double t = 0; for (int k = 0; k < 32; ++k) t += redd[k]; gpw[0] += (float)t; }
+  if (tid < 32) {                                                        // Linear2 bias gradient = sum_b gh2[b]
+    float v = 0.f; for (int b = tid; b < B; b += 32) v += s_g2[b];
+    v = warp_sum(v);
+    if (tid == 0) gb2[0] += v;
+  }
+}
+int d_head_bwd(const float* gout, const float* hsig, const float* hd, const float* h1o, const float* pw, const float* mask, const float* W2, float* gh1,
+               float* gW2, float* gb2, float* gpw, int B, int param_grads) {
+  if (B > 1024) return set_err(CG_ERR_UNSUPPORTED, "d_head_bwd: batch %d", B);
+  ctx().next_bytes = 4.0 * B * 256 * 4;
+  CG_LAUNCH(k_d_head_bwd, 1, 1024, 0, gout, hsig, hd, h1o, pw, mask, W2, gh1, gW2, gb2, gpw, B, param_grads); return CG_OK;
+}
 }  // namespace cg

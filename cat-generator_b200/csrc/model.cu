@@ -375,6 +375,7 @@ static int copy_channels(const float* src, float* dst, long rows, int Cs, int Cd
   long n = rows * Cs; CG_LAUNCH(k_copy_channels, grid1d(n, 256, 4), 256, 0, src, dst, n, Cs, Cd, coff, dir); return CG_OK;
 }
 
+static bool d_head_use_fused() { static const bool off = getenv("CATGEN_DHEAD_UNFUSED") != nullptr; return !off; }
 static bool stn_use_fused() { static const bool off = getenv("CATGEN_STN_UNFUSED") != nullptr; return ctx().conv_engine == 1 && !off; }
 static void stn_params(cg_model* m, cg_stn* s, StnFusedParams* p, StnFusedGrads* g) {
   const cg_layer &c1 = m->layers[s->c1], &c2 = m->layers[s->c2], &l1 = m->layers[s->l1], &l2 = m->layers[s->l2];
@@ -386,7 +387,7 @@ static void stn_params(cg_model* m, cg_stn* s, StnFusedParams* p, StnFusedGrads*
 static int stn_forward(cg_model* m, cg_stn* s, const float* in, int B) {
   int ch = s->ch, S = s->S, S2 = S / 2, S4 = S / 4, f = 16 * S4 * S4;
   s->in = in;
-  s->fused = stn_use_fused();
+  s->fused = stn_use_fused() && stn_fused_shape_ok(ch, S);
   if (s->fused) {   // stn_fused.cu: localisation network in one launch (one CTA per image, fp32), sampler in one launch
     long n2 = (long)B * S2 * S2 * 16;
     s->pool1 = FW(m, (size_t)B * S2 * S2 * ch); s->c1o = FW(m, n2); s->c2o = FW(m, n2); s->pool2 = FW(m, (size_t)B * f); s->l1o = FW(m, (size_t)B * 64);
@@ -500,11 +501,15 @@ static int D_forward_fused(cg_model* d, int B, const float* mk, float* sig_dev, 
   mk = mk_head + (long)B * 320;
   d->h1o = FW(d, (size_t)B * 256); d->ha1 = FW(d, (size_t)B * 256); d->hd = FW(d, (size_t)B * 256); NN(d->h1o); NN(d->ha1); NN(d->hd);
   CG_TRY(layer_fwd(d, d->h1, d->catd, d->h1o, B, 1, 1));
-  CG_TRY(prelu_fwd(d->h1o, d->P + d->hpw, d->ha1, (long)B * 256));
-  CG_TRY(mask_elems(d->ha1, mk, d->hd, (long)B * 256));
   d->h2o = FW(d, B); d->hsig = FW(d, B); NN(d->h2o); NN(d->hsig);
-  CG_TRY(layer_fwd(d, d->h2, d->hd, d->h2o, B, 1, 1));
-  CG_TRY(sigmoid_fwd(d->h2o, d->hsig, B));
+  d->head_fused = d_head_use_fused();
+  if (d->head_fused) CG_TRY(d_head_fwd(d->h1o, d->P + d->hpw, mk, d->P + d->layers[d->h2].oW, d->P + d->layers[d->h2].ob, d->hd, d->h2o, d->hsig, B));   // fuse_d.cu
+  else {
+    CG_TRY(prelu_fwd(d->h1o, d->P + d->hpw, d->ha1, (long)B * 256));
+    CG_TRY(mask_elems(d->ha1, mk, d->hd, (long)B * 256));
+    CG_TRY(layer_fwd(d, d->h2, d->hd, d->h2o, B, 1, 1));
+    CG_TRY(sigmoid_fwd(d->h2o, d->hsig, B));
+  }
   if (sig_dev) CG_CUDA(cudaMemcpyAsync(sig_dev, d->hsig, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
   if (pre_dev) CG_CUDA(cudaMemcpyAsync(pre_dev, d->h2o, sizeof(float) * B, cudaMemcpyDeviceToDevice, ctx().stream));
   return CG_OK;
@@ -562,6 +567,7 @@ int D_forward_dev(cg_model* d, const float* x_nchw, int B, float* sig_dev, float
   d->catd = FW(d, (size_t)B * 20480); NN(d->catd);
   CG_TRY(mask_channels(d->cat, mk, d->catd, B, 64, 320)); mk += (long)B * 320;
   d->h1o = FW(d, (size_t)B * 256); d->ha1 = FW(d, (size_t)B * 256); d->hd = FW(d, (size_t)B * 256); NN(d->h1o); NN(d->ha1); NN(d->hd);
+  d->head_fused = false;
   CG_TRY(layer_fwd(d, d->h1, d->catd, d->h1o, B, 1, 1));
   CG_TRY(prelu_fwd(d->h1o, d->P + d->hpw, d->ha1, (long)B * 256));
   CG_TRY(mask_elems(d->ha1, mk, d->hd, (long)B * 256));
@@ -657,10 +663,16 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
   const float* mk_br = d->masks + (long)B * 64;
   const float* mk_head = d->masks + (long)B * (64 * 4 + 128);
   const float* mk_fc = mk_head + (long)B * 320;
-  float* gh2 = BW(d, B); NN(gh2); CG_TRY(sigmoid_bwd(d->hsig, gout_dev, gh2, B));
-  float* ghd = BW(d, (size_t)B * 256); NN(ghd); CG_TRY(layer_bwd(d, d->h2, d->hd, gh2, ghd, B, 1, 1));
-  float* gha1 = BW(d, (size_t)B * 256); NN(gha1); CG_TRY(mask_elems(ghd, mk_fc, gha1, (long)B * 256));
-  float* gh1 = BW(d, (size_t)B * 256); NN(gh1); CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, PG(d, d->hpw), (long)B * 256));
+  float* gh1 = BW(d, (size_t)B * 256); NN(gh1);
+  if (d->head_fused && B <= 1024) {
+    CG_TRY(d_head_bwd(gout_dev, d->hsig, d->hd, d->h1o, d->P + d->hpw, mk_fc, d->P + d->layers[d->h2].oW, gh1, d->G + d->layers[d->h2].oW, d->G + d->layers[d->h2].ob,
+                      d->G + d->hpw, B, d->skip_param_grads ? 0 : 1));
+  } else {
+    float* gh2 = BW(d, B); NN(gh2); CG_TRY(sigmoid_bwd(d->hsig, gout_dev, gh2, B));
+    float* ghd = BW(d, (size_t)B * 256); NN(ghd); CG_TRY(layer_bwd(d, d->h2, d->hd, gh2, ghd, B, 1, 1));
+    float* gha1 = BW(d, (size_t)B * 256); NN(gha1); CG_TRY(mask_elems(ghd, mk_fc, gha1, (long)B * 256));
+    CG_TRY(prelu_bwd(d->h1o, gha1, d->P + d->hpw, gh1, PG(d, d->hpw), (long)B * 256));
+  }
   float* gcatd = BW(d, (size_t)B * 20480); NN(gcatd); CG_TRY(layer_bwd(d, d->h1, d->catd, gh1, gcatd, B, 1, 1));
   if (d->dfused && d->stn[0].fused && getenv("CATGEN_DBWD_UNFUSED") == nullptr) return D_backward_fused(d, gcatd, gx_nchw);
   float* gcat = BW(d, (size_t)B * 20480); NN(gcat); CG_TRY(mask_channels(gcatd, mk_head, gcat, B, 64, 320));
@@ -707,7 +719,8 @@ int D_backward_dev(cg_model* d, const float* gout_dev, float* gx_nchw) {
 
 namespace cg {
 // =================================================================== V (models.lua:765-804), evaluate() mode forward
-// activation = nn.LeakyReLU with no argument: negval = 1/100 (not D's 0.333)
+// activation = nn.LeakyReLU with no argument = the repository's own module (LeakyReLU.lua:5-10, negative_scale 0.333),
+// the same one D's localisation networks use.  (A newer upstream nn that already defines nn.LeakyReLU -- default 1/100 -- would win: LeakyReLU.lua:2-4.)
 int V_forward_dev(cg_model* v, const float* x_nchw, int B, float* out_dev) {
   SplitScope split_scope;
   CG_TRY(model_repack(v, 1));   // V's shapes are not in conv_tc_all_shapes_taken's list: keep the fp32 operands fresh for any layer the engine declines
@@ -728,7 +741,7 @@ int V_forward_dev(cg_model* v, const float* x_nchw, int B, float* out_dev) {
       r += 2 * co[i]; y = b;
     }
     float* a = FW(v, n); NN(a);
-    CG_TRY(lrelu_fwd(y, 0.01f, a, n));
+    CG_TRY(lrelu_fwd(y, 0.333f, a, n));
     cur = a;
     if (i != 2) {             // SpatialMaxPooling(2,2) after conv 1, 2 and 4
       float* p = FW(v, n / 4); uint8_t* idx = (uint8_t*)FW(v, n / 16 + 4); NN(p); NN(idx);
@@ -746,7 +759,7 @@ int V_forward_dev(cg_model* v, const float* x_nchw, int B, float* out_dev) {
     float* y = FW(v, (size_t)B * 1024); float* b = FW(v, (size_t)B * 1024); float* a = FW(v, (size_t)B * 1024); NN(y); NN(b); NN(a);
     CG_TRY(layer_fwd(v, v->vlin[i], cur, y, B, 1, 1));
     CG_TRY(bn_fwd_eval(y, v->P + v->vbn[2 + i], v->P + v->vbn[2 + i] + 1024, b, v->run + r, v->run + r + 1024, B, 1024, 1e-5f)); r += 2048;
-    CG_TRY(lrelu_fwd(b, 0.01f, a, (long)B * 1024));
+    CG_TRY(lrelu_fwd(b, 0.333f, a, (long)B * 1024));
     cur = a;
   }
   float* logit = FW(v, (size_t)B * 2); NN(logit);

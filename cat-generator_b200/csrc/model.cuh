@@ -54,6 +54,7 @@ struct cg_model {
   long t1pw, t2pw, bpw1[4], bpw2[4], hpw;
   float *xin, *tc1, *ta1, *tc2, *ta2, *tpool, *T, *bc1[4], *ba1[4], *bmp[4], *bdr[4], *bc2[4], *cat, *catd, *h1o, *ha1, *hd, *h2o, *hsig;
   uint8_t* bidx[4];
+  bool head_fused = false;                   // the last D forward ran the head (PReLU, Dropout, Linear(256,1), Sigmoid) as one kernel (fuse_d.cu d_head_fwd)
   bool dfused = false;                       // the last D forward ran the fused chains (fuse_d.cu): ta1, ta2, tpool, ba1, bmp, bdr, cat are not materialised
   const uint8_t *xq_t2 = nullptr, *xq_b4 = nullptr, *xq_b2[4] = {nullptr, nullptr, nullptr, nullptr};   // cached conv operands (forward + weight gradient)
   unsigned int* amax = nullptr;              // 16 words: max|gradient| recorded by producers for the next stage's fp16 packing scale (fuse_d.cu)
@@ -76,11 +77,16 @@ namespace cg {
 // fused spatial transformer (stn_fused.cu): parameter / gradient pointers into the flat Torch-layout vectors
 struct StnFusedParams { const float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; int ch, S, rot, scl, trn, nth; };
 struct StnFusedGrads { float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; };
+bool stn_fused_shape_ok(int ch, int S);
 inline int stn_fused_part_floats(int ch, int nth) { return 16 * ch * 9 + 16 + 16 * 16 * 9 + 16 + 64 + nth * 64 + nth; }
 int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* pool1, float* c1o, float* c2o, float* pool2, float* l1o, float* theta, float* A, float* out);
 int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const float* in, int B, const float* pool1, const float* c1o, const float* c2o, const float* pool2,
                        const float* l1o, const float* theta, const float* A, const float* gout, float* gin, float* ggrid, float* gl1, float* part, int skip_param_grads,
                        unsigned int* amax_out = nullptr);   // amax_out: also record max|gin| (float bits, atomicMax)
+// fuse_d.cu: the head of D32_st3 behind Linear(20480,256) in one launch per direction
+int d_head_fwd(const float* h1o, const float* pw, const float* mask, const float* W2, const float* b2, float* hd, float* h2o, float* hsig, int B);
+int d_head_bwd(const float* gout, const float* hsig, const float* hd, const float* h1o, const float* pw, const float* mask, const float* W2, float* gh1,
+               float* gW2, float* gb2, float* gpw, int B, int param_grads);
 // fuse_d.cu: PReLU -> [2x2 pool] -> dropout mask -> {dense fp32 / Concat slot / next conv's fp16 operand} in one pass over a conv output
 int act_pool_mask_pack(const float* y, const float* pw, int N, int H, int W, int C, int pool, const float* mask, int mask_stride, uint8_t* idx,
                        float* out, int out_stride, int out_off, uint8_t* xq, int k);

@@ -26,70 +26,129 @@ struct StnArgs {
   const float* in;                     // [B,S,S,ch]
   // saved by the forward (global)
   float *pool1, *c1o, *c2o, *pool2, *l1o, *theta, *A;
+  int dbg;                             // experiments (CATGEN_STN_DBG=1): block 0 records clock64 at every phase boundary
 };
+__device__ long long g_stn_dbg[32];
+#define STN_T(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) g_stn_dbg[k] = clock64(); } while (0)
 
-// 3x3 "same" convolution of a [P x P x Ci] tile in shared memory with weights in shared memory laid out [(tap, ci)][17] (16 + 1 pad:
-// conflict-free both with co across a warp's threads, here, and with ci across them, in the input gradient); thread ->
-// (pixel group, co).  out = bias + sum; written to out_s [P*P][16] (and out_g when non-null).
-__device__ __forceinline__ void conv3x3_16(const float* __restrict__ x_s, const float* __restrict__ w_s, const float* __restrict__ bias, float* __restrict__ out_s,
-                                            float* __restrict__ out_g, int P, int Ci) {
-  const int co = threadIdx.x & 15;
-  for (int p = threadIdx.x >> 4; p < P * P; p += blockDim.x >> 4) {
-    const int y = p / P, x = p - y * P;
-    float acc = bias[co];
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1; if (yy < 0 || yy >= P) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1; if (xx < 0 || xx >= P) continue;
-        const float* xr = x_s + (yy * P + xx) * Ci;
-        const float* wr = w_s + ((ky * 3 + kx) * Ci) * 17 + co;
-        // four independent chains (a single one ran at one FMA per shared-memory latency: the kernels were latency-bound at 8 warps per SM)
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f; int ci = 0;
-        for (; ci + 4 <= Ci; ci += 4) { a0 += xr[ci] * wr[ci * 17]; a1 += xr[ci + 1] * wr[(ci + 1) * 17]; a2 += xr[ci + 2] * wr[(ci + 2) * 17]; a3 += xr[ci + 3] * wr[(ci + 3) * 17]; }
-        for (; ci < Ci; ++ci) a0 += xr[ci] * wr[ci * 17];
-        acc += (a0 + a1) + (a2 + a3);
-      }
-    }
-    out_s[p * 16 + co] = acc;
-    if (out_g) out_g[p * 16 + co] = acc;
-  }
-}
-
-// shared-memory plan (floats): pool1 [P*P*ch] | a [P*P*16] | c [P*P*16] | w1 [9*ch*16] | w2 [9*16*16] | pool2 [f] | v64 [64] | misc [32]
-struct StnSmem { int pool1, a, c, w1, w2, pool2, v64, misc, total; };
-__host__ __device__ inline StnSmem stn_smem(int ch, int S) {
+// ---- localisation-network convolutions out of shared memory, round 2b.
+// The first fused version read one activation and one weight word from shared memory per FMA (2 LDS / FMA): with 16 warps per SM the
+// kernels were bound by shared-memory instruction issue and latency (CATGEN_STN_DBG=1, profiles/r02_stn_phases.txt: conv1 46k of 92k cycles
+// forward; the per-image weight gradient 112k / 222k of 241k / 421k cycles backward), and three transformer branches sharing an SM slowed each
+// other 3x.  Now: activations live in HALO'D buffers (no border branches), the channel index is contiguous and padded so that every operand
+// is fetched with 16-byte loads, each thread keeps several pixels (forward / input gradient) or 4 output channels x 9 taps (weight gradient)
+// in registers.  Shared-memory traffic per FMA drops 4-8x; the arithmetic is the same fp32 sums in a different (still fixed) order.
+//
+// shared-memory plan (floats).  CS1 = roundup(ch,4) + 4 and 20 = 16 + 4 are the padded channel strides (16-byte aligned, bank-staggered);
+// HP = (P+2)^2 halo'd pixels.
+struct StnSmem { int xh, a2h, g2h, cs, w1, w2, pool2, v64, misc, total, CS1, chp, HP; };
+__host__ __device__ inline StnSmem stn_smem(int ch, int S, bool bwd) {
   const int P = S / 2, f = 16 * (S / 4) * (S / 4);
-  StnSmem m; int o = 0;
-  m.pool1 = o; o += P * P * ch; m.a = o; o += P * P * 16; m.c = o; o += P * P * 16;
-  m.w1 = o; o += 9 * ch * 17; m.w2 = o; o += 9 * 16 * 17; m.pool2 = o; o += f; m.v64 = o; o += 64; m.misc = o; o += 32; m.total = o;
+  StnSmem m; m.chp = (ch + 3) & ~3; m.CS1 = m.chp + 4; m.HP = (P + 2) * (P + 2);
+  int o = 0;
+  m.xh = o; o += m.HP * m.CS1;                       // pooled input, halo'd   (backward: afterwards the plain [P*P][ch] input gradient)
+  m.a2h = o; o += m.HP * 20;                         // LeakyReLU(conv1), halo'd (backward: afterwards gc1, the gradient w.r.t. conv1's output)
+  m.g2h = o; o += bwd ? m.HP * 20 : 0;               // backward: gradient w.r.t. conv2's output, halo'd
+  m.cs = o; o += bwd ? 0 : P * P * 16;               // forward: conv2's output, plain
+  m.w1 = o; o += bwd ? 9 * m.chp * 20 : 9 * 16 * m.CS1;   // forward [tap][co][CS1] (ci contiguous); backward [tap][ci][20] (co contiguous)
+  m.w2 = o; o += 9 * 16 * 20;
+  m.pool2 = o; o += f; m.v64 = o; o += 64; m.misc = o; o += 64; m.total = o;
   return m;
 }
-__device__ __forceinline__ void load_conv_w(const float* __restrict__ W, float* __restrict__ w_s, int Ci) {   // Torch [16][Ci][3][3] -> [(tap,ci)][17]
-  for (int i = threadIdx.x; i < 16 * Ci * 9; i += blockDim.x) { int tap = i % 9, r = i / 9, ci = r % Ci, co = r / Ci; w_s[(tap * Ci + ci) * 17 + co] = W[i]; }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc)))); }
+__device__ __forceinline__ void smem_zero(float* sm, int n) {   // n multiple of 4
+  float4* q = reinterpret_cast<float4*>(sm);
+  for (int i = threadIdx.x; i < n / 4; i += blockDim.x) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// Torch [16][Ci][3][3] -> forward layout [tap][co][CS] (ci contiguous); eight loads in flight per thread
+__device__ __forceinline__ void load_w_fwd(const float* __restrict__ W, float* __restrict__ w_s, int Ci, int CS) {
+  const int n = 16 * Ci * 9;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? W[i] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int tap = i % 9, r = i / 9, ci = r % Ci, co = r / Ci; w_s[(tap * 16 + co) * CS + ci] = v[u]; } }
+  }
+}
+// Torch [16][Ci][3][3] -> input-gradient layout [tap][ci (nci rows)][20] (co contiguous)
+__device__ __forceinline__ void load_w_bwd(const float* __restrict__ W, float* __restrict__ w_s, int Ci, int nci) {
+  const int n = 16 * Ci * 9;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? W[i] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int tap = i % 9, r = i / 9, ci = r % Ci, co = r / Ci; w_s[(tap * nci + ci) * 20 + co] = v[u]; } }
+  }
+}
+// out[p][co] = bias[co] + sum_{tap, ci} w[tap][co][ci] * xh[p + tap][ci]   (xh halo'd: pixel (y,x) sits at (y+1,x+1)).  512 threads: co = tid & 15,
+// pixel group = tid >> 4; PX pixels per thread (P*P == 32*PX).  Per (tap, 4 channels): 1 + PX 16-byte loads for 4*PX FMAs.
+template <int PX, typename Emit>
+__device__ __forceinline__ void conv_fwd_v(const float* __restrict__ xh, const float* __restrict__ wf, const float* __restrict__ bias, int P, int CS, int C4, Emit emit) {
+  const int co = threadIdx.x & 15, pg = threadIdx.x >> 4, PW = P + 2;
+  float acc[PX]; int base[PX];
+  const float bv = bias[co];
+#pragma unroll
+  for (int i = 0; i < PX; ++i) { const int p = pg + 32 * i, y = p / P, x = p - y * P; base[i] = (y * PW + x) * CS; acc[i] = bv; }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int off = ((tap / 3) * PW + (tap % 3)) * CS;
+    const float4* wr = reinterpret_cast<const float4*>(wf + (tap * 16 + co) * CS);
+    for (int c4 = 0; c4 < C4; ++c4) {
+      const float4 w = wr[c4];
+#pragma unroll
+      for (int i = 0; i < PX; ++i) acc[i] = dot4(w, *reinterpret_cast<const float4*>(xh + base[i] + off + 4 * c4), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PX; ++i) emit(pg + 32 * i, co, acc[i]);
 }
 
 __device__ __forceinline__ void atm_eval(const float* th, int rot, int scl, int trn, float* M6);   // ops.cu formulas, restated below
 
 __global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
-  extern __shared__ float sm[];
-  const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q;
-  const StnSmem m = stn_smem(ch, S);
-  float *pool1 = sm + m.pool1, *as = sm + m.a, *cs = sm + m.c, *w1 = sm + m.w1, *w2 = sm + m.w2, *pool2 = sm + m.pool2, *v64 = sm + m.v64;
-  load_conv_w(a.W1, w1, ch); load_conv_w(a.W2, w2, 16);
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q, PW = P + 2;
+  const StnSmem m = stn_smem(ch, S, false);
+  float *xh = sm + m.xh, *a2h = sm + m.a2h, *cs = sm + m.cs, *w1 = sm + m.w1, *w2 = sm + m.w2, *pool2 = sm + m.pool2, *v64 = sm + m.v64;
+  STN_T(0);
+  smem_zero(sm, m.w2);                                                    // halos, channel padding and weight padding (everything below w2 is fully written)
+  __syncthreads();
+  load_w_fwd(a.W1, w1, ch, m.CS1); load_w_fwd(a.W2, w2, 16, 20);
   const float* in = a.in + (size_t)b * S * S * ch;
-  for (int i = tid; i < P * P * ch; i += blockDim.x) {                     // nn.SpatialAveragePooling(2,2,2,2)
-    int c = i % ch, p = i / ch, y = p / P, x = p - y * P;
-    const float* s0 = in + ((size_t)(2 * y) * S + 2 * x) * ch + c;
-    float v = (s0[0] + s0[ch] + s0[(size_t)S * ch] + s0[(size_t)S * ch + ch]) * 0.25f;
-    pool1[i] = v; a.pool1[(size_t)b * P * P * ch + i] = v;
+  float* p1g = a.pool1 + (size_t)b * P * P * ch;
+  for (int i0 = tid; i0 < P * P * ch; i0 += 4 * blockDim.x) {             // nn.SpatialAveragePooling(2,2,2,2); sixteen loads in flight per thread
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x; v[u] = 0.f;
+      if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; const float* s0 = in + ((size_t)(2 * y) * S + 2 * x) * ch + c;
+        v[u] = (s0[0] + s0[ch] + s0[(size_t)S * ch] + s0[(size_t)S * ch + ch]) * 0.25f; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; p1g[i] = v[u]; }
+    }
   }
   __syncthreads();
-  conv3x3_16(pool1, w1, a.b1, cs, a.c1o + (size_t)b * P * P * 16, P, ch);
+  STN_T(1);
+  {
+    float* c1g = a.c1o + (size_t)b * P * P * 16;
+    auto emit = [&](int p, int co, float v) { const int y = p / P, x = p - y * P; c1g[p * 16 + co] = v; a2h[((y + 1) * PW + x + 1) * 20 + co] = lrelu_f(v); };
+    if (P == 8) conv_fwd_v<2>(xh, w1, a.b1, P, m.CS1, m.chp / 4, emit); else conv_fwd_v<8>(xh, w1, a.b1, P, m.CS1, m.chp / 4, emit);
+  }
   __syncthreads();
-  for (int i = tid; i < P * P * 16; i += blockDim.x) as[i] = lrelu_f(cs[i]);
+  STN_T(2);
+  STN_T(3);
+  {
+    float* c2g = a.c2o + (size_t)b * P * P * 16;
+    auto emit = [&](int p, int co, float v) { c2g[p * 16 + co] = v; cs[p * 16 + co] = v; };
+    if (P == 8) conv_fwd_v<2>(a2h, w2, a.b2, P, 20, 4, emit); else conv_fwd_v<8>(a2h, w2, a.b2, P, 20, 4, emit);
+  }
   __syncthreads();
-  conv3x3_16(as, w2, a.b2, cs, a.c2o + (size_t)b * P * P * 16, P, 16);
-  __syncthreads();
+  STN_T(4);
   for (int i = tid; i < f; i += blockDim.x) {                              // LeakyReLU then AvgPool2 -> [Q][Q][16]
     int c = i & 15, p = i >> 4, y = p / Q, x = p - y * Q;
     const float* s0 = cs + ((2 * y) * P + 2 * x) * 16 + c;
@@ -97,17 +156,18 @@ __global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
     pool2[i] = v; a.pool2[(size_t)b * f + i] = v;
   }
   __syncthreads();
-  {   // nn.View + nn.Linear(f, 64): Torch feature index ft = c*Q*Q + s for our [s][c].  One warp per output row, lanes over consecutive
-      // ft (coalesced weight reads), fixed shuffle tree
-    // (a single dependent chain of L2 loads per warp made this loop 60 of the kernel's 85 us: four rows at a time, four loads each in flight)
+  STN_T(5);
+  {   // nn.View + nn.Linear(f, 64): Torch feature index ft = c*Q*Q + s for our [s][c].  One warp per four output rows, lanes over consecutive
+      // ft (coalesced weight reads), four loads in flight, fixed shuffle tree
     const int warp = tid >> 5, lane = tid & 31, QQ = Q * Q, nw = (int)(blockDim.x >> 5);
     for (int o0 = warp * 4; o0 < 64; o0 += nw * 4) {
       const float* Wr = a.L1 + (size_t)o0 * f;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
       for (int ft = lane; ft < f; ft += 32) {
         const int c = ft / QQ, s2 = ft - c * QQ; const float pv = pool2[s2 * 16 + c];
-        const float w0 = Wr[ft], w1 = Wr[(size_t)f + ft], w2 = Wr[(size_t)2 * f + ft], w3 = Wr[(size_t)3 * f + ft];
-        acc[0] += pv * w0; acc[1] += pv * w1; acc[2] += pv * w2; acc[3] += pv * w3;
+        const float w0 = Wr[ft], w1v = Wr[(size_t)f + ft], w2v = Wr[(size_t)2 * f + ft], w3 = Wr[(size_t)3 * f + ft];
+        acc[0] += pv * w0; acc[1] += pv * w1v; acc[2] += pv * w2v; acc[3] += pv * w3;
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -117,6 +177,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
     }
   }
   __syncthreads();
+  STN_T(6);
   if (tid < a.nth) {                                                       // nn.Linear(64, n_theta)
     float acc = a.lb2[tid];
     for (int i = 0; i < 64; ++i) acc += v64[i] * a.L2[tid * 64 + i];
@@ -124,6 +185,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
   }
   __syncthreads();
   if (tid == 0) { float M6[6]; atm_eval(sm + m.misc, a.rot, a.scl, a.trn, M6); for (int i = 0; i < 6; ++i) a.A[(size_t)b * 6 + i] = M6[i]; }
+  STN_T(7);
 }
 
 // nn.AffineTransformMatrixGenerator: I * R(alpha) * S(s) * T(tx,ty), first two rows; R = [[c,-s],[s,c]] (ops.cu k_atm_fwd)
@@ -238,6 +300,7 @@ struct StnBwdArgs {
   unsigned int* amax_out;              // optional: max|gin| after both branches were summed (float bits)
   int np_part;                         // = 16*ch*9 + 16 + 16*16*9 + 16 + 64 + nth*64 + nth   (W1,b1,W2,b2,lb1,L2,lb2; L1's weight goes through gl1)
 };
+
 __device__ __forceinline__ float block_sum_f(float v, float* scratch) {   // fixed order; result valid in every thread
   v = warp_sum(v);
   __syncthreads();
@@ -247,60 +310,85 @@ __device__ __forceinline__ float block_sum_f(float v, float* scratch) {   // fix
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += scratch[i];
   return r;
 }
-// input gradient of a 3x3 "same" conv: gx[p][ci] = sum_{tap,co} gy[p - tap + 1][co] * W[co][ci][tap]; weights in smem as [(tap,ci)][16]
-__device__ __forceinline__ void conv3x3_dgrad(const float* __restrict__ gy_s, const float* __restrict__ w_s, float* __restrict__ gx_s, int P, int Ci) {
-  for (int i = threadIdx.x; i < P * P * Ci; i += blockDim.x) {
-    const int ci = i % Ci, p = i / Ci, y = p / P, x = p - y * P;
-    float acc = 0.f;
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y - ky + 1; if (yy < 0 || yy >= P) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x - kx + 1; if (xx < 0 || xx >= P) continue;
-        const float* g = gy_s + (yy * P + xx) * 16;
-        const float* wr = w_s + ((ky * 3 + kx) * Ci + ci) * 17;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// gx[p][ci] = sum_{tap, co} wd[tap][ci][co] * gyh[p + (2-ky, 2-kx)][co]  (gyh halo'd).  Threads: ci = tid % nci, pixel group = tid / nci;
+// PX pixels per thread (PX * 512 / nci == P*P).  Per (tap, 4 co): 1 + PX 16-byte loads for 4*PX FMAs.
+template <int PX, typename Emit>
+__device__ __forceinline__ void conv_dgrad_v(const float* __restrict__ gyh, const float* __restrict__ wd, int P, int nci, Emit emit) {
+  const int ci = threadIdx.x % nci, g = threadIdx.x / nci, ng = (int)blockDim.x / nci, PW = P + 2;
+  float acc[PX]; int base[PX];
 #pragma unroll
-        for (int co = 0; co < 16; co += 4) { a0 += g[co] * wr[co]; a1 += g[co + 1] * wr[co + 1]; a2 += g[co + 2] * wr[co + 2]; a3 += g[co + 3] * wr[co + 3]; }
-        acc += (a0 + a1) + (a2 + a3);
-      }
+  for (int i = 0; i < PX; ++i) { const int p = g + ng * i, y = p / P, x = p - y * P; base[i] = (y * PW + x) * 20; acc[i] = 0.f; }
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {                                     // (fully unrolled, ptxas hoisted 288 16-byte loads and spilled)
+    const int off = ((2 - tap / 3) * PW + (2 - tap % 3)) * 20;
+    const float4* wr = reinterpret_cast<const float4*>(wd + (tap * nci + ci) * 20);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = wr[q];
+#pragma unroll
+      for (int i = 0; i < PX; ++i) acc[i] = dot4(w, *reinterpret_cast<const float4*>(gyh + base[i] + off + 4 * q), acc[i]);
     }
-    gx_s[i] = acc;
   }
+#pragma unroll
+  for (int i = 0; i < PX; ++i) emit(g + ng * i, ci, acc[i]);
 }
-// per-image weight-gradient partial of a 3x3 conv in TORCH layout: gW[co][ci][ky][kx] = sum_p gy[p][co] * x[p + tap - 1][ci]; gb[co] = sum_p gy[p][co].
-// thread <-> (co, ci) pair with all nine taps in registers: a warp's threads share co (broadcast read of gy) and read consecutive ci of x.
-__device__ __forceinline__ void conv3x3_wgrad(const float* __restrict__ x_s, const float* __restrict__ gy_s, float* __restrict__ gW, float* __restrict__ gb, int P, int Ci) {
-  for (int e = threadIdx.x; e < 16 * Ci; e += blockDim.x) {
-    const int ci = e % Ci, co = e / Ci;
-    float acc[9];
+// per-image weight-gradient partial in TORCH layout: gW[co][ci][tap] = sum_p gy[p][co] * x[p + tap - 1][ci].  A task = (ci, 2 output channels) with the
+// nine taps of each in registers; SL adjacent lanes split the pixels of a task and are summed by a fixed shuffle tree.
+// Per pixel: one 8-byte load of gy + 9 loads of x for 18 FMAs.
+template <int SL>
+__device__ __forceinline__ void conv_wgrad_v(const float* __restrict__ xh, int CSx, const float* __restrict__ gyh, float* __restrict__ gW, int P, int Ci) {
+  // (two output channels per task: four -- 36 accumulators -- spilled under the 128-register cap of a 512-thread block)
+  const int t = threadIdx.x / SL, sl = threadIdx.x % SL, PW = P + 2;
+  const bool active = t < Ci * 8;                                           // whole SL-groups are active or idle; idle lanes still take part in the shuffles
+  const int ci = active ? t % Ci : 0, cop = active ? t / Ci : 0;            // cop: pair of output channels
+  float acc[2][9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-    for (int y = 0; y < P; ++y)
-      for (int x = 0; x < P; ++x) {
-        const float g = gy_s[(y * P + x) * 16 + co];
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int yy = y + ky - 1; if (yy < 0 || yy >= P) continue;
+    for (int q = 0; q < 9; ++q) acc[j][q] = 0.f;
+  if (active) for (int p = sl; p < P * P; p += SL) {
+    const int y = p / P, x = p - y * P;
+    const float2 g = *reinterpret_cast<const float2*>(gyh + ((y + 1) * PW + x + 1) * 20 + cop * 2);
+    const float* xb = xh + (y * PW + x) * CSx + ci;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1; if (xx < 0 || xx >= P) continue;
-            acc[ky * 3 + kx] += g * x_s[(yy * P + xx) * Ci + ci];
-          }
-        }
-      }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) gW[(size_t)e * 9 + t] = acc[t];
+    for (int q = 0; q < 9; ++q) {
+      const float xv = xb[((q / 3) * PW + q % 3) * CSx];
+      acc[0][q] = fmaf(g.x, xv, acc[0][q]); acc[1][q] = fmaf(g.y, xv, acc[1][q]);
+    }
   }
-  for (int co = threadIdx.x; co < 16; co += blockDim.x) { float acc = 0.f; for (int p = 0; p < P * P; ++p) acc += gy_s[p * 16 + co]; gb[co] = acc; }
+#pragma unroll
+  for (int o = SL / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) acc[j][q] += __shfl_xor_sync(0xffffffffu, acc[j][q], o);
+  if (active && sl == 0)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) gW[((size_t)(cop * 2 + j) * Ci + ci) * 9 + q] = acc[j][q];
+}
+// gb[co] = sum_p gy[p][co]: warp co, lanes over pixels, fixed shuffle tree
+__device__ __forceinline__ void bias_grad_v(const float* __restrict__ gyh, float* __restrict__ gb, int P) {
+  const int co = threadIdx.x >> 5, lane = threadIdx.x & 31, PW = P + 2;
+  if (co < 16) {
+    float v = 0.f;
+    for (int p = lane; p < P * P; p += 32) { const int y = p / P, x = p - y * P; v += gyh[((y + 1) * PW + x + 1) * 20 + co]; }
+    v = warp_sum(v);
+    if (lane == 0) gb[co] = v;
+  }
 }
 
 __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const StnArgs& a = q.f;
-  const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q, nth = a.nth;
-  const StnSmem m = stn_smem(ch, S);
-  float *pool1 = sm + m.pool1, *as = sm + m.a, *cs = sm + m.c, *w1 = sm + m.w1, *w2 = sm + m.w2, *pool2 = sm + m.pool2, *v64 = sm + m.v64, *misc = sm + m.misc;
-  load_conv_w(a.W1, w1, ch); load_conv_w(a.W2, w2, 16);
+  const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q, nth = a.nth, PW = P + 2;
+  const StnSmem m = stn_smem(ch, S, true);
+  float *xh = sm + m.xh, *a2h = sm + m.a2h, *g2h = sm + m.g2h, *w1 = sm + m.w1, *w2 = sm + m.w2, *pool2 = sm + m.pool2, *v64 = sm + m.v64, *misc = sm + m.misc;
+  STN_T(0);
+  smem_zero(sm, m.pool2);
+  __syncthreads();
+  load_w_bwd(a.W1, w1, ch, m.chp); load_w_bwd(a.W2, w2, 16, 16);
   float* part = q.part ? q.part + (size_t)b * q.np_part : nullptr;
   const int oW1 = 0, ob1 = oW1 + 16 * ch * 9, oW2 = ob1 + 16, ob2 = oW2 + 16 * 16 * 9, olb1 = ob2 + 16, oL2 = olb1 + 64, olb2 = oL2 + nth * 64;
   // ---- AffineGridGeneratorBHWD backward: gA = sum_pixels ggrid^T * (y_i, x_j, 1), fixed-order block reduction (ops.cu k_grid_bwd)
@@ -322,6 +410,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
     }
     __syncthreads();
   }
+  STN_T(1);
   // ---- Linear(64, nth) backward: v64 <- lrelu(l1o); gal1 = L2^T gtheta; partials gL2 = gtheta (x) al1, glb2 = gtheta
   const float* l1o = a.l1o + (size_t)b * 64;
   if (tid < 64) {
@@ -334,11 +423,12 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
   }
   if (part && tid < nth) part[olb2 + tid] = misc[8 + tid];
   __syncthreads();
+  STN_T(2);
   // ---- Linear(f, 64) backward (input gradient): gpool2[s][c] = sum_o L1[o][c*Q*Q + s] * gl1[o]
   for (int ft = tid; ft < f; ft += blockDim.x) {                           // consecutive threads read consecutive weights of each row
     const int c = ft / (Q * Q), s2 = ft - c * Q * Q;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                            // four independent chains: four L2 loads in flight per thread
-#pragma unroll 4
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                            // four independent chains: eight L2 loads in flight per thread
+#pragma unroll 2
     for (int o = 0; o < 64; o += 4) {
       a0 += a.L1[(size_t)o * f + ft] * v64[o]; a1 += a.L1[(size_t)(o + 1) * f + ft] * v64[o + 1];
       a2 += a.L1[(size_t)(o + 2) * f + ft] * v64[o + 2]; a3 += a.L1[(size_t)(o + 3) * f + ft] * v64[o + 3];
@@ -346,40 +436,82 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
     pool2[s2 * 16 + c] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  // ---- AvgPool2 backward + LeakyReLU backward: gc2 (in cs) = lrelu'(c2o) * gpool2 / 4
+  STN_T(3);
+  // ---- AvgPool2 backward + LeakyReLU backward: gc2 (g2h) = lrelu'(c2o) * gpool2 / 4;  a1 = lrelu(c1o) (a2h) = conv2's input; pooled input (xh)
   const float* c2o = a.c2o + (size_t)b * P * P * 16; const float* c1o = a.c1o + (size_t)b * P * P * 16;
-  for (int i = tid; i < P * P * 16; i += blockDim.x) {
-    const int c = i & 15, p = i >> 4, y = p / P, x = p - y * P;
-    cs[i] = lrelu_g(c2o[i], pool2[((y >> 1) * Q + (x >> 1)) * 16 + c] * 0.25f);
-    as[i] = lrelu_f(c1o[i]);                                               // a1 = conv2's input
+  for (int i0 = tid; i0 < P * P * 16; i0 += 4 * blockDim.x) {
+    float u2[4], u1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; const bool ok = i < P * P * 16; u2[u] = ok ? c2o[i] : 0.f; u1[u] = ok ? c1o[i] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < P * P * 16) {
+        const int c = i & 15, p = i >> 4, y = p / P, x = p - y * P, h = ((y + 1) * PW + x + 1) * 20 + c;
+        g2h[h] = lrelu_g(u2[u], pool2[((y >> 1) * Q + (x >> 1)) * 16 + c] * 0.25f);
+        a2h[h] = lrelu_f(u1[u]);
+      }
+    }
+  }
+  const float* p1g = a.pool1 + (size_t)b * P * P * ch;
+  for (int i0 = tid; i0 < P * P * ch; i0 += 4 * blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < P * P * ch ? p1g[i] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; } }
   }
   __syncthreads();
-  if (part) conv3x3_wgrad(as, cs, part + oW2, part + ob2, P, 16);
+  STN_T(4);
+  if (part) { conv_wgrad_v<4>(a2h, 20, g2h, part + oW2, P, 16); bias_grad_v(g2h, part + ob2, P); }
   __syncthreads();
-  // ---- conv2 input gradient ga1 -> `as` (a1 is no longer needed once conv2's weight gradient is done)
-  conv3x3_dgrad(cs, w2, as, P, 16);
+  STN_T(5);
+  // ---- conv2 input gradient, LeakyReLU backward on the way: gc1 -> a2h (a1 is no longer needed once conv2's weight gradient is done)
+  {
+    auto emit = [&](int p, int ci, float v) { const int y = p / P, x = p - y * P; a2h[((y + 1) * PW + x + 1) * 20 + ci] = lrelu_g(c1o[p * 16 + ci], v); };
+    if (P == 8) conv_dgrad_v<2>(g2h, w2, P, 16, emit); else conv_dgrad_v<8>(g2h, w2, P, 16, emit);
+  }
   __syncthreads();
-  for (int i = tid; i < P * P * 16; i += blockDim.x) cs[i] = lrelu_g(c1o[i], as[i]);   // gc1
-  const float* p1g = a.pool1 + (size_t)b * P * P * ch;
-  for (int i = tid; i < P * P * ch; i += blockDim.x) pool1[i] = p1g[i];
+  STN_T(6);
+  STN_T(7);
+  if (part) {
+    if (ch >= 64) conv_wgrad_v<1>(xh, m.CS1, a2h, part + oW1, P, ch); else conv_wgrad_v<16>(xh, m.CS1, a2h, part + oW1, P, ch);   // ch <= 4: 8*ch tasks x 16 lanes
+    bias_grad_v(a2h, part + ob1, P);
+  }
   __syncthreads();
-  if (part) conv3x3_wgrad(pool1, cs, part + oW1, part + ob1, P, ch);
+  STN_T(8);
+  // ---- conv1 input gradient (plain [p][ch], into the xh region: the pooled input was consumed by the weight gradient above)
+  {
+    float* gp1 = xh;
+    auto emit = [&](int p, int ci, float v) { if (ci < ch) gp1[p * ch + ci] = v; };
+    if (m.chp == 64) conv_dgrad_v<8>(a2h, w1, P, 64, emit);             // P == 8
+    else conv_dgrad_v<2>(a2h, w1, P, 4, emit);                          // P == 16, ch <= 4
+  }
   __syncthreads();
-  // ---- conv1 input gradient, then AvgPool2 backward ADDED into the sampler's input gradient (the two ConcatTable branches sum)
-  conv3x3_dgrad(cs, w1, pool1, P, ch);                                      // pool1 <- gpool1 (its forward values were consumed above)
-  __syncthreads();
+  STN_T(9);
+  // ---- AvgPool2 backward ADDED into the sampler's input gradient (the two ConcatTable branches sum)
   float* gin = q.gin + (size_t)b * S * S * ch;
   float amx = 0.f;
-  for (int i = tid; i < S * S * ch; i += blockDim.x) {
-    const int c = i % ch, p = i / ch, y = p / S, x = p - y * S;
-    const float v = gin[i] + pool1[((y >> 1) * P + (x >> 1)) * ch + c] * 0.25f;
-    gin[i] = v; amx = fmaxf(amx, fabsf(v));
+  for (int i0 = tid; i0 < S * S * ch; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < S * S * ch ? gin[i] : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < S * S * ch) {
+        const int c = i % ch, p = i / ch, y = p / S, x = p - y * S;
+        const float r = v[u] + xh[((y >> 1) * P + (x >> 1)) * ch + c] * 0.25f;
+        gin[i] = r; amx = fmaxf(amx, fabsf(r));
+      }
+    }
   }
   if (q.amax_out) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
     if ((tid & 31) == 0 && amx > 0.f) atomicMax(q.amax_out, __float_as_uint(amx));
   }
+  STN_T(10);
 }
 
 // fixed-order sum of the per-image partials over the batch + Linear1's weight gradient (sum over the batch of gl1 (x) pool2), accumulated
@@ -422,21 +554,33 @@ __global__ void k_stn_param_reduce(StnRedArgs r) {
 }
 
 // ---------------------------------------------------------------- host side
-static size_t stn_smem_bytes(int ch, int S) { return sizeof(float) * (size_t)stn_smem(ch, S).total; }
+static size_t stn_smem_bytes(int ch, int S, bool bwd) { return sizeof(float) * (size_t)stn_smem(ch, S, bwd).total; }
+bool stn_fused_shape_ok(int ch, int S) { return (S == 16 && ch == 64) || (S == 32 && ch >= 1 && ch <= 4); }   // the register tilings above are written for these
+static bool stn_dbg_on() { static const bool on = getenv("CATGEN_STN_DBG") != nullptr; return on; }
+static void stn_dbg_print(const char* what, int ch, int S, int B, int n) {
+  cudaStreamSynchronize(ctx().stream);
+  long long h[32]; cudaMemcpyFromSymbol(h, g_stn_dbg, sizeof(h));
+  fprintf(stderr, "[stn dbg] %s ch=%d S=%d B=%d total %lld cycles; phases:", what, ch, S, B, h[n] - h[0]);
+  for (int i = 1; i <= n; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+  fprintf(stderr, "\n");
+}
 static int stn_set_attr() {
   static bool done = false;
   if (done) return CG_OK;
-  CG_CUDA(cudaFuncSetAttribute(k_stn_loc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CG_CUDA(cudaFuncSetAttribute(k_stn_loc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CG_CUDA(cudaFuncSetAttribute(k_stn_loc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  CG_CUDA(cudaFuncSetAttribute(k_stn_loc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   done = true; return CG_OK;
 }
 int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* pool1, float* c1o, float* c2o, float* pool2, float* l1o, float* theta, float* A, float* out) {
+  if (!stn_fused_shape_ok(p.ch, p.S)) return set_err(CG_ERR_UNSUPPORTED, "fused spatial transformer: ch=%d S=%d", p.ch, p.S);
   CG_TRY(stn_set_attr());
   StnArgs a{};
   a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2;
   a.B = B; a.ch = p.ch; a.S = p.S; a.rot = p.rot; a.scl = p.scl; a.trn = p.trn; a.nth = p.nth; a.in = in;
   a.pool1 = pool1; a.c1o = c1o; a.c2o = c2o; a.pool2 = pool2; a.l1o = l1o; a.theta = theta; a.A = A;
-  CG_LAUNCH(k_stn_loc_fwd, B, 512, stn_smem_bytes(p.ch, p.S), a);
+  a.dbg = stn_dbg_on() ? 1 : 0;
+  CG_LAUNCH(k_stn_loc_fwd, B, 512, stn_smem_bytes(p.ch, p.S, false), a);
+  if (a.dbg) stn_dbg_print("loc_fwd [w+pool1, conv1, lrelu, conv2, pool2, linear1, linear2+atm]", p.ch, p.S, B, 7);
   long npix = (long)B * p.S * p.S;
   ctx().next_bytes = 8.0 * (double)npix * p.ch;
   CG_LAUNCH(k_stn_sample_fwd, cdiv(npix * 32, 256), 256, 0, in, (const float*)A, out, npix, p.S, p.S, p.ch);
@@ -457,7 +601,9 @@ int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const fl
   a.pool1 = const_cast<float*>(pool1); a.c1o = const_cast<float*>(c1o); a.c2o = const_cast<float*>(c2o); a.pool2 = const_cast<float*>(pool2);
   a.l1o = const_cast<float*>(l1o); a.theta = const_cast<float*>(theta); a.A = const_cast<float*>(A);
   q.ggrid = ggrid; q.gin = gin; q.gl1 = gl1; q.np_part = stn_fused_part_floats(p.ch, p.nth); q.part = skip_param_grads ? nullptr : part; q.amax_out = amax_out;
-  CG_LAUNCH(k_stn_loc_bwd, B, 512, stn_smem_bytes(p.ch, p.S), q);
+  a.dbg = stn_dbg_on() ? 1 : 0;
+  CG_LAUNCH(k_stn_loc_bwd, B, 512, stn_smem_bytes(p.ch, p.S, true), q);
+  if (a.dbg) stn_dbg_print(skip_param_grads ? "loc_bwd(no wgrad) [w+grid, l2, l1 dgrad, pool/lrelu, wgrad2, dgrad2, gc1, wgrad1, dgrad1, gin]" : "loc_bwd [w+grid, l2, l1 dgrad, pool/lrelu, wgrad2, dgrad2, gc1, wgrad1, dgrad1, gin]", p.ch, p.S, B, 10);
   if (!skip_param_grads) {
     StnRedArgs r{};
     const int Q = p.S / 4;

@@ -300,7 +300,7 @@ def V32_init(C_img, seed):
 
 def V_forward(flat, running, x):
     """MODEL_V:forward(images) in evaluate() mode (train.lua:123; utils/nn_utils.lua:700), NCHW, through the oracle's
-    operators: conv-LeakyReLU(1/100)-maxpool, conv-BN-LReLU-maxpool-Dropout(id), conv-LReLU, conv-BN-LReLU-maxpool-
+    operators: conv-LeakyReLU(0.333)-maxpool, conv-BN-LReLU-maxpool-Dropout(id), conv-LReLU, conv-BN-LReLU-maxpool-
     SpatialDropout(x0.5)-View, Linear-BN-LReLU-Dropout(id) x2, Linear-SoftMax (models.lua:769-799).  Returns [B,2]."""
     L = lib()
     x = np.ascontiguousarray(x, np.float32)
@@ -332,7 +332,7 @@ def V_forward(flat, running, x):
 
     def lrelu(h):
         y = np.empty_like(h)
-        L.og_leakyrelu_fwd(P(h), 0.01, P(y), h.size)
+        L.og_leakyrelu_fwd(P(h), 0.333, P(y), h.size)   # LeakyReLU.lua:5-10 (row A8), as in D's localisation networks
         return y
 
     def pool(h):

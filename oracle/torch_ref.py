@@ -140,14 +140,14 @@ def V_forward(flat, running, x, C=3):
         W, b = c.take(co, ci, 3, 3), c.take(co)
         return F.conv2d(h, W, b, padding=1)
 
-    h = F.max_pool2d(F.leaky_relu(conv(x, C, 128), 0.01), 2)
-    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 128, 128), 128), 0.01), 2)
-    h = F.leaky_relu(conv(h, 128, 256), 0.01)
-    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 256, 256), 256), 0.01), 2) * 0.5
+    h = F.max_pool2d(F.leaky_relu(conv(x, C, 128), 0.333), 2)
+    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 128, 128), 128), 0.333), 2)
+    h = F.leaky_relu(conv(h, 128, 256), 0.333)
+    h = F.max_pool2d(F.leaky_relu(bn(conv(h, 256, 256), 256), 0.333), 2) * 0.5
     h = h.reshape(B, 4096)
     for _ in range(2):
         W, b = c.take(1024, h.shape[1]), c.take(1024)
-        h = F.leaky_relu(bn(F.linear(h, W, b), 1024), 0.01)
+        h = F.leaky_relu(bn(F.linear(h, W, b), 1024), 0.333)
     W, b = c.take(2, 1024), c.take(2)
     h = F.linear(h, W, b)
     assert c.o == flat.numel() and r.o == running.numel()

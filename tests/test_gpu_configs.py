@@ -44,7 +44,7 @@ def test_closures_match_oracle_at_baseline_size(gk, ok, Cc, B):
     Bounds: generated pixels <= 1e-3 max-abs (north_star); D's sigmoid outputs <= 1e-3; closure losses <= 2e-3;
     gradients relative to max|oracle| as gtol below (the fp16 forward of G moves PReLU decisions; see test_gpu_parity's
     module docstring, statement (c))."""
-    _closures_vs_oracle(gk, ok, Cc, B, "", px=1e-3, dout=1e-3, loss=2e-3, gD=8e-2, gG=5e-2)
+    _closures_vs_oracle(gk, ok, Cc, B, "", b_px=1e-3, b_out=1e-3, b_loss=2e-3, b_gD=8e-2, b_gG=5e-2)
 
 
 def test_closures_with_compensated_forward_operands_c2():
@@ -54,12 +54,12 @@ def test_closures_with_compensated_forward_operands_c2():
     lib.check(L.cg_set_precision(1))
     try:
         assert L.cg_get_precision() == 1
-        _closures_vs_oracle(lib.G32UPC, po.G32UPC, 3, 128, " precision=1", px=1e-4, dout=1e-4, loss=2e-4, gD=1e-2, gG=1e-2)
+        _closures_vs_oracle(lib.G32UPC, po.G32UPC, 3, 128, " precision=1", b_px=1e-4, b_out=1e-4, b_loss=2e-4, b_gD=1e-2, b_gG=1e-2)
     finally:
         lib.check(L.cg_set_precision(0))
 
 
-def _closures_vs_oracle(gk, ok, Cc, B, tag, px, dout, loss, gD, gG):
+def _closures_vs_oracle(gk, ok, Cc, B, tag, b_px, b_out, b_loss, b_gD, b_gG):
     L = lib.load()
     rng = np.random.default_rng(50 + B)
     og, od = po.Model(ok, Cc, 100, seed=1), po.Model(po.D32_ST3, Cc, 100, seed=2)
@@ -75,16 +75,16 @@ def _closures_vs_oracle(gk, ok, Cc, B, tag, px, dout, loss, gD, gG):
     f0 = po.lib().og_fevalD(ot.h, C.byref(ocfg), po.P(np.concatenate([real, fake0]).astype(np.float32)), po.P(targets), po.P(maskD), po.P(dout0))
     e_out, e_gD = float(np.abs(out - dout0).max()), rel(gD, od.grads)
     _report("fevalD B=%d%s" % (B, tag), pixels=e_px, d_out=e_out, loss=abs(f - f0), gradD_rel_max=e_gD, gradD_l2=l2rel(gD, od.grads))
-    assert e_px < px and e_out < dout and abs(f - f0) < loss
-    assert e_gD < gD          # default precision: fp16 forward of D flips PReLU / max-pool decisions (test_gpu_parity module docstring, statement (c)); measured 4.9e-2 .. 6.1e-2 of max, L2 1.8e-2 .. 2.2e-2
+    assert e_px < b_px and e_out < b_out and abs(f - f0) < b_loss
+    assert e_gD < b_gD        # default precision: fp16 forward of D flips PReLU / max-pool decisions (test_gpu_parity module docstring, statement (c)); measured 4.9e-2 .. 6.1e-2 of max, L2 1.8e-2 .. 2.2e-2
     # fevalG_on_D with D's parameters as they are (no update in between: gradients, not trajectories, carry the claim)
     g.set_bn_running(og.bn_running)
     outG, fG, gimg, gG = _gpu_fevalG(L, g, d, cfg, zG, maskG, B)
     fG0 = po.lib().og_fevalG_on_D(ot.h, C.byref(ocfg), po.P(zG), po.P(maskG))
     e_gG = rel(gG, og.grads)
     _report("fevalG B=%d%s" % (B, tag), loss=abs(fG - fG0), gradG_rel_max=e_gG, gradG_l2=l2rel(gG, og.grads))
-    assert abs(fG - fG0) < loss
-    assert e_gG < gG
+    assert abs(fG - fG0) < b_loss
+    assert e_gG < b_gG
 
 
 def test_c3_fused_step_with_two_D_iterations_tracks_oracle():

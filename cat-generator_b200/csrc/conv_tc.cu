@@ -282,11 +282,12 @@ __global__ void k_repack_model(const PackJob* __restrict__ jobs, int njobs, int 
   const ConvSpec s = J.s;
   const long tid = (blockIdx.x - J.blk0) * (long)blockDim.x + threadIdx.x, nth = (long)J.nblk * blockDim.x;
   const long n = (long)s.k * s.k * s.Ci * s.Co;
-  if (mode & 1) for (long i = tid; i < n; i += nth) {     // Wp[(ky,kx,ci)][co]
+  const bool m32 = (mode & 1) || J.always32;
+  if (m32) for (long i = tid; i < n; i += nth) {     // Wp[(ky,kx,ci)][co]
     int co = (int)(i % s.Co); long r = i / s.Co; int ci = (int)(r % s.Ci); int tap = (int)(r / s.Ci);
     J.Wp[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, tap / s.k, tap % s.k, ci, co)];
   }
-  if ((mode & 1) && J.need_dgrad) for (long i = tid; i < n; i += nth) {     // Wd[(ky,kx,co)][ci], taps flipped
+  if (m32 && J.need_dgrad) for (long i = tid; i < n; i += nth) {     // Wd[(ky,kx,co)][ci], taps flipped
     int ci = (int)(i % s.Ci); long r = i / s.Ci; int co = (int)(r % s.Co); int tap = (int)(r / s.Co);
     J.Wd[i] = J.W[torch_index(s.k, s.Ci, s.Co, s.in_hw, s.out_hw, s.k - 1 - tap / s.k, s.k - 1 - tap % s.k, ci, co)];
   }

@@ -134,13 +134,14 @@ int model_build(cg_model* m) {
     for (size_t i = 0; i < m->layers.size(); ++i) {
       cg_layer& L = m->layers[i]; cg::PackJob& J = jobs[i];
       J.W = m->P + L.oW; J.b = m->P + L.ob; J.Wp = L.Wp; J.Wd = L.Wd; J.bp = L.bp; J.s = L.s; J.need_dgrad = L.need_dgrad ? 1 : 0;
-      J.wqf = J.wqd = nullptr; J.CBf = J.CBd = 0;
+      J.wqf = J.wqd = nullptr; J.CBf = J.CBd = 0; J.always32 = 0;
       { long nW = (long)L.s.Co * L.s.Ci * L.s.k * L.s.k; J.blk0 = m->repack_blocks; J.nblk = (int)((nW + 2047) / 2048); m->repack_blocks += J.nblk; }
       size_t bf = 0, bd = 0;
       const bool plain = L.s.in_hw == 1 && L.s.out_hw == 1;     // Linear layers beside an nn.View (k = 1) are taken by the round-2 engine only (CB == 32)
       if (conv_tc_wslice_plan(L.s.Ci, L.s.Co, L.s.k, &J.CBf, &bf) && (plain || J.CBf == 32)) { J.wqf = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bf + 255) & ~(size_t)255; }
       if (L.need_dgrad && conv_tc_wslice_plan(L.s.Co, L.s.Ci, L.s.k, &J.CBd, &bd) && (plain || J.CBd == 32)) { J.wqd = (uint8_t*)(uintptr_t)(wq_total + 1); wq_total += (bd + 255) & ~(size_t)255; }
     }
+    if (m->kind == CG_D32_ST3) for (int q = 0; q < 4; ++q) { jobs[m->stn[q].c1].always32 = 1; jobs[m->stn[q].c2].always32 = 1; }   // read by stn_fused.cu in fp32
     if (wq_total) CG_CUDA(cudaMalloc(&m->wq, wq_total));
     for (size_t i = 0; i < jobs.size(); ++i) {   // offsets (+1 so that offset 0 is distinguishable from "none") -> pointers
       cg::PackJob& J = jobs[i];
@@ -380,6 +381,7 @@ static bool stn_use_fused() { static const bool off = getenv("CATGEN_STN_UNFUSED
 static void stn_params(cg_model* m, cg_stn* s, StnFusedParams* p, StnFusedGrads* g) {
   const cg_layer &c1 = m->layers[s->c1], &c2 = m->layers[s->c2], &l1 = m->layers[s->l1], &l2 = m->layers[s->l2];
   p->W1 = m->P + c1.oW; p->b1 = m->P + c1.ob; p->W2 = m->P + c2.oW; p->b2 = m->P + c2.ob;
+  p->W1p = c1.Wp; p->W1d = c1.Wd; p->W2p = c2.Wp; p->W2d = c2.Wd;   // packed fp32 operands (k_repack_model, always32)
   p->L1 = m->P + l1.oW; p->lb1 = m->P + l1.ob; p->L2 = m->P + l2.oW; p->lb2 = m->P + l2.ob;
   p->ch = s->ch; p->S = s->S; p->rot = s->rot; p->scl = s->scl; p->trn = s->trn; p->nth = s->nth;
   if (g) { g->W1 = m->G + c1.oW; g->b1 = m->G + c1.ob; g->W2 = m->G + c2.oW; g->b2 = m->G + c2.ob; g->L1 = m->G + l1.oW; g->lb1 = m->G + l1.ob; g->L2 = m->G + l2.oW; g->lb2 = m->G + l2.ob; }

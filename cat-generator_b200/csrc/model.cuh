@@ -75,7 +75,8 @@ struct cg_trainer {
 
 namespace cg {
 // fused spatial transformer (stn_fused.cu): parameter / gradient pointers into the flat Torch-layout vectors
-struct StnFusedParams { const float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; int ch, S, rot, scl, trn, nth; };
+struct StnFusedParams { const float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; int ch, S, rot, scl, trn, nth;
+                        const float *W1p, *W1d, *W2p, *W2d; };   // the convolutions' packed fp32 operands: Wp[(tap,ci)][co], Wd[(flipped tap,co)][ci]
 struct StnFusedGrads { float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2; };
 bool stn_fused_shape_ok(int ch, int S);
 inline int stn_fused_part_floats(int ch, int nth) { return 16 * ch * 9 + 16 + 16 * 16 * 9 + 16 + 64 + nth * 64 + nth; }

@@ -116,6 +116,7 @@ struct PackJob {
   const float *W, *b; float *Wp, *Wd, *bp; uint8_t *wqf, *wqd;   // wqf/wqd null: not a tensor-core layer
   ConvSpec s; int need_dgrad, CBf, CBd;
   int blk0, nblk;                                                 // this job's slice of the flat grid (blocks proportional to its weight count)
+  int always32;                                                   // the fp32 operands Wp / Wd are refreshed on EVERY repack (the fused spatial transformer reads them: stn_fused.cu)
 };
 int repack_model(const PackJob* jobs_dev, int njobs, int total_blocks, int mode);   // mode: 1 fp32 operands, 2 bias + fp16 slices, 3 both
 bool conv_tc_all_shapes_taken(int B);   // true when every conv / Linear call at batch B goes to the tensor-core engine (no fp32 operand is read)

@@ -22,6 +22,7 @@ __device__ __forceinline__ float lrelu_g(float x, float g) { return x >= 0.f ? g
 struct StnArgs {
   // parameters, Torch layout (flat parameter vector)
   const float *W1, *b1, *W2, *b2, *L1, *lb1, *L2, *lb2;
+  const float *W1p, *W1d, *W2p, *W2d;   // packed fp32 operands of the two convolutions (conv_ref.cu layouts): Wp[(tap,ci)][co], Wd[(8-tap,co)][ci]
   int B, ch, S, rot, scl, trn, nth;
   const float* in;                     // [B,S,S,ch]
   // saved by the forward (global)
@@ -60,26 +61,32 @@ __device__ __forceinline__ void smem_zero(float* sm, int n) {   // n multiple of
   float4* q = reinterpret_cast<float4*>(sm);
   for (int i = threadIdx.x; i < n / 4; i += blockDim.x) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-// Torch [16][Ci][3][3] -> forward layout [tap][co][CS] (ci contiguous); eight loads in flight per thread
-__device__ __forceinline__ void load_w_fwd(const float* __restrict__ W, float* __restrict__ w_s, int Ci, int CS) {
-  const int n = 16 * Ci * 9;
+// Index arithmetic: the divisors (channels, P, S) are run-time values and a 32-bit division costs ~40 instructions -- the element-wise
+// loops of the first version spent most of their cycles dividing (profiles/r02_stn_phases.txt, phases "w+pool1", "gin").  Powers of two shift.
+struct Dv { int d, sh; };
+__device__ __forceinline__ Dv mk_dv(int d) { Dv v; v.d = d; v.sh = (d & (d - 1)) == 0 ? 31 - __clz(d) : -1; return v; }
+__device__ __forceinline__ int dv_div(int i, const Dv& v) { return v.sh >= 0 ? i >> v.sh : i / v.d; }
+__device__ __forceinline__ int dv_mod(int i, const Dv& v) { return v.sh >= 0 ? i & (v.d - 1) : i % v.d; }
+// forward layout [tap][co][CS] (ci contiguous) from the packed input-gradient operand Wd[(8-tap, co)][ci] (taps flipped): row copies
+__device__ __forceinline__ void load_w_fwd(const float* __restrict__ Wd, float* __restrict__ w_s, int Ci, int CS) {
+  const int n = 9 * 16 * Ci; const Dv dc = mk_dv(Ci);
   for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
     float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? W[i] : 0.f; }
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? Wd[i] : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int tap = i % 9, r = i / 9, ci = r % Ci, co = r / Ci; w_s[(tap * 16 + co) * CS + ci] = v[u]; } }
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int row = dv_div(i, dc), ci = dv_mod(i, dc); w_s[((8 - (row >> 4)) * 16 + (row & 15)) * CS + ci] = v[u]; } }
   }
 }
-// Torch [16][Ci][3][3] -> input-gradient layout [tap][ci (nci rows)][20] (co contiguous)
-__device__ __forceinline__ void load_w_bwd(const float* __restrict__ W, float* __restrict__ w_s, int Ci, int nci) {
-  const int n = 16 * Ci * 9;
+// input-gradient layout [tap][ci (nci rows)][20] (co contiguous) from the packed forward operand Wp[(tap, ci)][co]: row copies
+__device__ __forceinline__ void load_w_bwd(const float* __restrict__ Wp, float* __restrict__ w_s, int Ci, int nci) {
+  const int n = 9 * Ci * 16; const Dv dc = mk_dv(Ci);
   for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
     float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? W[i] : 0.f; }
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < n ? Wp[i] : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int tap = i % 9, r = i / 9, ci = r % Ci, co = r / Ci; w_s[(tap * nci + ci) * 20 + co] = v[u]; } }
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) { const int r = i >> 4, tap = dv_div(r, dc), ci = dv_mod(r, dc); w_s[(tap * nci + ci) * 20 + (i & 15)] = v[u]; } }
   }
 }
 // out[p][co] = bias[co] + sum_{tap, ci} w[tap][co][ci] * xh[p + tap][ci]   (xh halo'd: pixel (y,x) sits at (y+1,x+1)).  512 threads: co = tid & 15,
@@ -89,12 +96,14 @@ __device__ __forceinline__ void conv_fwd_v(const float* __restrict__ xh, const f
   const int co = threadIdx.x & 15, pg = threadIdx.x >> 4, PW = P + 2;
   float acc[PX]; int base[PX];
   const float bv = bias[co];
+  const int lP = 31 - __clz(P);                                           // P is 8 or 16 (stn_fused_shape_ok)
 #pragma unroll
-  for (int i = 0; i < PX; ++i) { const int p = pg + 32 * i, y = p / P, x = p - y * P; base[i] = (y * PW + x) * CS; acc[i] = bv; }
+  for (int i = 0; i < PX; ++i) { const int p = pg + 32 * i, y = p >> lP, x = p - y * P; base[i] = (y * PW + x) * CS; acc[i] = bv; }
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int off = ((tap / 3) * PW + (tap % 3)) * CS;
     const float4* wr = reinterpret_cast<const float4*>(wf + (tap * 16 + co) * CS);
+#pragma unroll 4
     for (int c4 = 0; c4 < C4; ++c4) {
       const float4 w = wr[c4];
 #pragma unroll
@@ -115,28 +124,29 @@ __global__ void __launch_bounds__(512) k_stn_loc_fwd(StnArgs a) {
   STN_T(0);
   smem_zero(sm, m.w2);                                                    // halos, channel padding and weight padding (everything below w2 is fully written)
   __syncthreads();
-  load_w_fwd(a.W1, w1, ch, m.CS1); load_w_fwd(a.W2, w2, 16, 20);
+  load_w_fwd(a.W1d, w1, ch, m.CS1); load_w_fwd(a.W2d, w2, 16, 20);
   const float* in = a.in + (size_t)b * S * S * ch;
   float* p1g = a.pool1 + (size_t)b * P * P * ch;
+  const Dv dch = mk_dv(ch), dP = mk_dv(P);
   for (int i0 = tid; i0 < P * P * ch; i0 += 4 * blockDim.x) {             // nn.SpatialAveragePooling(2,2,2,2); sixteen loads in flight per thread
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * blockDim.x; v[u] = 0.f;
-      if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; const float* s0 = in + ((size_t)(2 * y) * S + 2 * x) * ch + c;
+      if (i < P * P * ch) { const int c = dv_mod(i, dch), p = dv_div(i, dch), y = dv_div(p, dP), x = p - y * P; const float* s0 = in + ((size_t)(2 * y) * S + 2 * x) * ch + c;
         v[u] = (s0[0] + s0[ch] + s0[(size_t)S * ch] + s0[(size_t)S * ch + ch]) * 0.25f; }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * blockDim.x;
-      if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; p1g[i] = v[u]; }
+      if (i < P * P * ch) { const int c = dv_mod(i, dch), p = dv_div(i, dch), y = dv_div(p, dP), x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; p1g[i] = v[u]; }
     }
   }
   __syncthreads();
   STN_T(1);
   {
     float* c1g = a.c1o + (size_t)b * P * P * 16;
-    auto emit = [&](int p, int co, float v) { const int y = p / P, x = p - y * P; c1g[p * 16 + co] = v; a2h[((y + 1) * PW + x + 1) * 20 + co] = lrelu_f(v); };
+    auto emit = [&](int p, int co, float v) { const int y = dv_div(p, dP), x = p - y * P; c1g[p * 16 + co] = v; a2h[((y + 1) * PW + x + 1) * 20 + co] = lrelu_f(v); };
     if (P == 8) conv_fwd_v<2>(xh, w1, a.b1, P, m.CS1, m.chp / 4, emit); else conv_fwd_v<8>(xh, w1, a.b1, P, m.CS1, m.chp / 4, emit);
   }
   __syncthreads();
@@ -242,8 +252,11 @@ __device__ __forceinline__ void grid_at(const float* A6, int i, int j, int H, in
   float yb = -1.f + 2.f * i / (H - 1), xb = -1.f + 2.f * j / (W - 1);
   gy = A6[0] * yb + A6[1] * xb + A6[2]; gx = A6[3] * yb + A6[4] * xb + A6[5];
 }
+// LPP lanes share a pixel and stride over its channels: 32 for the 64-channel branch transformers, 4 for the 1- / 3-channel input transformer
+// (with a whole warp per pixel 29 of 32 lanes idled there: 45 us forward, 69 us backward for 1.5 MB of image, profiles/r02_timeline.txt)
+template <int LPP>
 __global__ void k_stn_sample_fwd(const float* __restrict__ img, const float* __restrict__ A, float* __restrict__ out, long npix, int H, int W, int C) {
-  long pix = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  long pix = (blockIdx.x * (long)blockDim.x + threadIdx.x) / LPP; int lane = threadIdx.x % LPP;
   if (pix >= npix) return;
   long b = pix / ((long)H * W); int r = (int)(pix - b * H * W), ii = r / W, jj = r - ii * W;
   float gy_, gx_; grid_at(A + b * 6, ii, jj, H, W, gy_, gx_);
@@ -252,7 +265,7 @@ __global__ void k_stn_sample_fwd(const float* __restrict__ img, const float* __r
   float wy = 1.f - (yc - fy), wx = 1.f - (xc - fx);
   bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H, vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
   const float* base = img + b * H * W * C;
-  for (int c = lane; c < C; c += 32) {
+  for (int c = lane; c < C; c += LPP) {
     float a00 = (vy0 && vx0) ? base[((long)y0 * W + x0) * C + c] : 0.f;
     float a01 = (vy0 && vx1) ? base[((long)y0 * W + x0 + 1) * C + c] : 0.f;
     float a10 = (vy1 && vx0) ? base[((long)(y0 + 1) * W + x0) * C + c] : 0.f;
@@ -262,10 +275,12 @@ __global__ void k_stn_sample_fwd(const float* __restrict__ img, const float* __r
 }
 // backward of the sampler: scatter-add into gimg (fp32 atomics, as ops.cu k_bil_bwd and for the reason given there) and the
 // per-pixel gradient w.r.t. the grid point, which the localisation backward reduces per image in fixed order
+template <int LPP>
 __global__ void k_stn_sample_bwd(const float* __restrict__ img, const float* __restrict__ A, const float* __restrict__ gout,
                                  float* __restrict__ gimg, float* __restrict__ ggrid, long npix, int H, int W, int C) {
-  long pix = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
-  if (pix >= npix) return;
+  long pix = (blockIdx.x * (long)blockDim.x + threadIdx.x) / LPP; int lane = threadIdx.x % LPP;
+  const bool live = pix < npix;                                            // no early return: every lane takes part in the shuffles below
+  if (!live) pix = npix - 1;
   long b = pix / ((long)H * W); int r = (int)(pix - b * H * W), ii = r / W, jj = r - ii * W;
   float gy_, gx_; grid_at(A + b * 6, ii, jj, H, W, gy_, gx_);
   float yc = (gy_ + 1.f) * (H - 1) / 2.f, xc = (gx_ + 1.f) * (W - 1) / 2.f;
@@ -274,15 +289,18 @@ __global__ void k_stn_sample_bwd(const float* __restrict__ img, const float* __r
   bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H, vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
   const float* base = img + b * H * W * C; float* gb = gimg + b * H * W * C;
   float d00 = 0, d01 = 0, d10 = 0, d11 = 0;
-  for (int c = lane; c < C; c += 32) {
+  if (live) for (int c = lane; c < C; c += LPP) {
     float gv = gout[pix * C + c];
     if (vy0 && vx0) { long o = ((long)y0 * W + x0) * C + c; atomicAdd(gb + o, wx * wy * gv); d00 += base[o] * gv; }
     if (vy0 && vx1) { long o = ((long)y0 * W + x0 + 1) * C + c; atomicAdd(gb + o, (1.f - wx) * wy * gv); d01 += base[o] * gv; }
     if (vy1 && vx0) { long o = ((long)(y0 + 1) * W + x0) * C + c; atomicAdd(gb + o, wx * (1.f - wy) * gv); d10 += base[o] * gv; }
     if (vy1 && vx1) { long o = ((long)(y0 + 1) * W + x0 + 1) * C + c; atomicAdd(gb + o, (1.f - wx) * (1.f - wy) * gv); d11 += base[o] * gv; }
   }
-  d00 = warp_sum(d00); d01 = warp_sum(d01); d10 = warp_sum(d10); d11 = warp_sum(d11);
-  if (lane == 0) {
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) {                                   // fixed tree over the LPP lanes of this pixel
+    d00 += __shfl_xor_sync(0xffffffffu, d00, o); d01 += __shfl_xor_sync(0xffffffffu, d01, o); d10 += __shfl_xor_sync(0xffffffffu, d10, o); d11 += __shfl_xor_sync(0xffffffffu, d11, o);
+  }
+  if (live && lane == 0) {
     float gyf = -wx * d00 + wx * d10 - (1.f - wx) * d01 + (1.f - wx) * d11;
     float gxf = -wy * d00 + wy * d01 - (1.f - wy) * d10 + (1.f - wy) * d11;
     ggrid[pix * 2] = gyf * (H - 1) / 2.f;
@@ -317,7 +335,7 @@ __device__ __forceinline__ void conv_dgrad_v(const float* __restrict__ gyh, cons
   const int ci = threadIdx.x % nci, g = threadIdx.x / nci, ng = (int)blockDim.x / nci, PW = P + 2;
   float acc[PX]; int base[PX];
 #pragma unroll
-  for (int i = 0; i < PX; ++i) { const int p = g + ng * i, y = p / P, x = p - y * P; base[i] = (y * PW + x) * 20; acc[i] = 0.f; }
+  for (int i = 0; i < PX; ++i) { const int p = g + ng * i, y = p >> (31 - __clz(P)), x = p - y * P; base[i] = (y * PW + x) * 20; acc[i] = 0.f; }
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {                                     // (fully unrolled, ptxas hoisted 288 16-byte loads and spilled)
     const int off = ((2 - tap / 3) * PW + (2 - tap % 3)) * 20;
@@ -347,7 +365,7 @@ __device__ __forceinline__ void conv_wgrad_v(const float* __restrict__ xh, int C
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[j][q] = 0.f;
   if (active) for (int p = sl; p < P * P; p += SL) {
-    const int y = p / P, x = p - y * P;
+    const int y = p >> (31 - __clz(P)), x = p - y * P;
     const float2 g = *reinterpret_cast<const float2*>(gyh + ((y + 1) * PW + x + 1) * 20 + cop * 2);
     const float* xb = xh + (y * PW + x) * CSx + ci;
 #pragma unroll
@@ -373,7 +391,7 @@ __device__ __forceinline__ void bias_grad_v(const float* __restrict__ gyh, float
   const int co = threadIdx.x >> 5, lane = threadIdx.x & 31, PW = P + 2;
   if (co < 16) {
     float v = 0.f;
-    for (int p = lane; p < P * P; p += 32) { const int y = p / P, x = p - y * P; v += gyh[((y + 1) * PW + x + 1) * 20 + co]; }
+    for (int p = lane; p < P * P; p += 32) { const int y = p >> (31 - __clz(P)), x = p - y * P; v += gyh[((y + 1) * PW + x + 1) * 20 + co]; }
     v = warp_sum(v);
     if (lane == 0) gb[co] = v;
   }
@@ -385,10 +403,11 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
   const int b = blockIdx.x, tid = threadIdx.x, ch = a.ch, S = a.S, P = S / 2, Q = S / 4, f = 16 * Q * Q, nth = a.nth, PW = P + 2;
   const StnSmem m = stn_smem(ch, S, true);
   float *xh = sm + m.xh, *a2h = sm + m.a2h, *g2h = sm + m.g2h, *w1 = sm + m.w1, *w2 = sm + m.w2, *pool2 = sm + m.pool2, *v64 = sm + m.v64, *misc = sm + m.misc;
+  const Dv dch = mk_dv(ch), dP = mk_dv(P), dS = mk_dv(S);
   STN_T(0);
   smem_zero(sm, m.pool2);
   __syncthreads();
-  load_w_bwd(a.W1, w1, ch, m.chp); load_w_bwd(a.W2, w2, 16, 16);
+  load_w_bwd(a.W1p, w1, ch, m.chp); load_w_bwd(a.W2p, w2, 16, 16);
   float* part = q.part ? q.part + (size_t)b * q.np_part : nullptr;
   const int oW1 = 0, ob1 = oW1 + 16 * ch * 9, oW2 = ob1 + 16, ob2 = oW2 + 16 * 16 * 9, olb1 = ob2 + 16, oL2 = olb1 + 64, olb2 = oL2 + nth * 64;
   // ---- AffineGridGeneratorBHWD backward: gA = sum_pixels ggrid^T * (y_i, x_j, 1), fixed-order block reduction (ops.cu k_grid_bwd)
@@ -396,7 +415,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
     float s6[6] = {0, 0, 0, 0, 0, 0};
     const float* gg = q.ggrid + (size_t)b * S * S * 2;
     for (int i = tid; i < S * S; i += blockDim.x) {
-      int ii = i / S, j = i - ii * S;
+      int ii = i >> (31 - __clz(S)), j = i - ii * S;                          // S is 16 or 32
       float yb = -1.f + 2.f * ii / (S - 1), xb = -1.f + 2.f * j / (S - 1);
       float g0 = gg[i * 2], g1 = gg[i * 2 + 1];
       s6[0] += g0 * yb; s6[1] += g0 * xb; s6[2] += g0; s6[3] += g1 * yb; s6[4] += g1 * xb; s6[5] += g1;
@@ -425,15 +444,29 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
   __syncthreads();
   STN_T(2);
   // ---- Linear(f, 64) backward (input gradient): gpool2[s][c] = sum_o L1[o][c*Q*Q + s] * gl1[o]
-  for (int ft = tid; ft < f; ft += blockDim.x) {                           // consecutive threads read consecutive weights of each row
-    const int c = ft / (Q * Q), s2 = ft - c * Q * Q;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                            // four independent chains: eight L2 loads in flight per thread
-#pragma unroll 2
-    for (int o = 0; o < 64; o += 4) {
-      a0 += a.L1[(size_t)o * f + ft] * v64[o]; a1 += a.L1[(size_t)(o + 1) * f + ft] * v64[o + 1];
-      a2 += a.L1[(size_t)(o + 2) * f + ft] * v64[o + 2]; a3 += a.L1[(size_t)(o + 3) * f + ft] * v64[o + 3];
+  {
+    // consecutive threads read consecutive weights of a row; the 64 rows are split over G = blockDim / f thread groups when f < blockDim
+    // (f = 256: every thread has 32 rows, 16 loads in flight), partial sums combined in group order through the (still unused) g2h region
+    const int G = f < (int)blockDim.x ? (int)blockDim.x / f : 1, rows = 64 / G;
+    float* scr = g2h;                                                       // G * f floats <= 1024 (HP * 20 >= 2000)
+    for (int e = tid; e < f * G; e += blockDim.x) {
+      const int ft = e % f, gq = e / f, o0 = gq * rows;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int o = o0; o < o0 + rows; o += 4) {
+        a0 += a.L1[(size_t)o * f + ft] * v64[o]; a1 += a.L1[(size_t)(o + 1) * f + ft] * v64[o + 1];
+        a2 += a.L1[(size_t)(o + 2) * f + ft] * v64[o + 2]; a3 += a.L1[(size_t)(o + 3) * f + ft] * v64[o + 3];
+      }
+      scr[e] = (a0 + a1) + (a2 + a3);
     }
-    pool2[s2 * 16 + c] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    for (int ft = tid; ft < f; ft += blockDim.x) {
+      const int c = ft / (Q * Q), s2 = ft - c * Q * Q;
+      float v = 0.f; for (int gq = 0; gq < G; ++gq) v += scr[gq * f + ft];
+      pool2[s2 * 16 + c] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < f * G; e += blockDim.x) scr[e] = 0.f;              // g2h must be all zero again (its halo is never written)
   }
   __syncthreads();
   STN_T(3);
@@ -447,7 +480,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * blockDim.x;
       if (i < P * P * 16) {
-        const int c = i & 15, p = i >> 4, y = p / P, x = p - y * P, h = ((y + 1) * PW + x + 1) * 20 + c;
+        const int c = i & 15, p = i >> 4, y = dv_div(p, dP), x = p - y * P, h = ((y + 1) * PW + x + 1) * 20 + c;
         g2h[h] = lrelu_g(u2[u], pool2[((y >> 1) * Q + (x >> 1)) * 16 + c] * 0.25f);
         a2h[h] = lrelu_f(u1[u]);
       }
@@ -459,7 +492,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < P * P * ch ? p1g[i] : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < P * P * ch) { const int c = i % ch, p = i / ch, y = p / P, x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; } }
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < P * P * ch) { const int c = dv_mod(i, dch), p = dv_div(i, dch), y = dv_div(p, dP), x = p - y * P; xh[((y + 1) * PW + x + 1) * m.CS1 + c] = v[u]; } }
   }
   __syncthreads();
   STN_T(4);
@@ -468,7 +501,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
   STN_T(5);
   // ---- conv2 input gradient, LeakyReLU backward on the way: gc1 -> a2h (a1 is no longer needed once conv2's weight gradient is done)
   {
-    auto emit = [&](int p, int ci, float v) { const int y = p / P, x = p - y * P; a2h[((y + 1) * PW + x + 1) * 20 + ci] = lrelu_g(c1o[p * 16 + ci], v); };
+    auto emit = [&](int p, int ci, float v) { const int y = dv_div(p, dP), x = p - y * P; a2h[((y + 1) * PW + x + 1) * 20 + ci] = lrelu_g(c1o[p * 16 + ci], v); };
     if (P == 8) conv_dgrad_v<2>(g2h, w2, P, 16, emit); else conv_dgrad_v<8>(g2h, w2, P, 16, emit);
   }
   __syncthreads();
@@ -500,7 +533,7 @@ __global__ void __launch_bounds__(512) k_stn_loc_bwd(StnBwdArgs q) {
     for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * blockDim.x;
       if (i < S * S * ch) {
-        const int c = i % ch, p = i / ch, y = p / S, x = p - y * S;
+        const int c = dv_mod(i, dch), p = dv_div(i, dch), y = dv_div(p, dS), x = p - y * S;
         const float r = v[u] + xh[((y >> 1) * P + (x >> 1)) * ch + c] * 0.25f;
         gin[i] = r; amx = fmaxf(amx, fabsf(r));
       }
@@ -575,7 +608,7 @@ int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* po
   if (!stn_fused_shape_ok(p.ch, p.S)) return set_err(CG_ERR_UNSUPPORTED, "fused spatial transformer: ch=%d S=%d", p.ch, p.S);
   CG_TRY(stn_set_attr());
   StnArgs a{};
-  a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2;
+  a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2; a.W1p = p.W1p; a.W1d = p.W1d; a.W2p = p.W2p; a.W2d = p.W2d;
   a.B = B; a.ch = p.ch; a.S = p.S; a.rot = p.rot; a.scl = p.scl; a.trn = p.trn; a.nth = p.nth; a.in = in;
   a.pool1 = pool1; a.c1o = c1o; a.c2o = c2o; a.pool2 = pool2; a.l1o = l1o; a.theta = theta; a.A = A;
   a.dbg = stn_dbg_on() ? 1 : 0;
@@ -583,7 +616,8 @@ int stn_fused_forward(const StnFusedParams& p, const float* in, int B, float* po
   if (a.dbg) stn_dbg_print("loc_fwd [w+pool1, conv1, lrelu, conv2, pool2, linear1, linear2+atm]", p.ch, p.S, B, 7);
   long npix = (long)B * p.S * p.S;
   ctx().next_bytes = 8.0 * (double)npix * p.ch;
-  CG_LAUNCH(k_stn_sample_fwd, cdiv(npix * 32, 256), 256, 0, in, (const float*)A, out, npix, p.S, p.S, p.ch);
+  if (p.ch <= 4) CG_LAUNCH(k_stn_sample_fwd<4>, cdiv(npix * 4, 256), 256, 0, in, (const float*)A, out, npix, p.S, p.S, p.ch);
+  else CG_LAUNCH(k_stn_sample_fwd<32>, cdiv(npix * 32, 256), 256, 0, in, (const float*)A, out, npix, p.S, p.S, p.ch);
   return CG_OK;
 }
 // gout [B,S,S,ch] -> gin [B,S,S,ch] (written); parameter gradients accumulated into g* unless skip_param_grads
@@ -593,10 +627,11 @@ int stn_fused_backward(const StnFusedParams& p, const StnFusedGrads& g, const fl
   long npix = (long)B * p.S * p.S;
   CG_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)npix * p.ch, ctx().stream));
   ctx().next_bytes = 12.0 * (double)npix * p.ch;
-  CG_LAUNCH(k_stn_sample_bwd, cdiv(npix * 32, 256), 256, 0, in, A, gout, gin, ggrid, npix, p.S, p.S, p.ch);
+  if (p.ch <= 4) CG_LAUNCH(k_stn_sample_bwd<4>, cdiv(npix * 4, 256), 256, 0, in, A, gout, gin, ggrid, npix, p.S, p.S, p.ch);
+  else CG_LAUNCH(k_stn_sample_bwd<32>, cdiv(npix * 32, 256), 256, 0, in, A, gout, gin, ggrid, npix, p.S, p.S, p.ch);
   StnBwdArgs q{};
   StnArgs& a = q.f;
-  a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2;
+  a.W1 = p.W1; a.b1 = p.b1; a.W2 = p.W2; a.b2 = p.b2; a.L1 = p.L1; a.lb1 = p.lb1; a.L2 = p.L2; a.lb2 = p.lb2; a.W1p = p.W1p; a.W1d = p.W1d; a.W2p = p.W2p; a.W2d = p.W2d;
   a.B = B; a.ch = p.ch; a.S = p.S; a.rot = p.rot; a.scl = p.scl; a.trn = p.trn; a.nth = p.nth; a.in = in;
   a.pool1 = const_cast<float*>(pool1); a.c1o = const_cast<float*>(c1o); a.c2o = const_cast<float*>(c2o); a.pool2 = const_cast<float*>(pool2);
   a.l1o = const_cast<float*>(l1o); a.theta = const_cast<float*>(theta); a.A = const_cast<float*>(A);

@@ -61,6 +61,24 @@ static int make_patch_tmap(CUtensorMap* tm, const void* xq, int ES, int N, int C
   return CG_OK;
 }
 
+// DUO tiles (8 x 8 images): one 128-row tile = TWO images, their rows interleaved in the shared-memory patch as [plane][h][j = image of the pair][w],
+// so that the tile's sixteen 8-pixel row groups (h, j) sit at a constant stride and a filter tap is still a shifted start address.  With the
+// plain 8 x 16 tile an 8-row image filled half of every MMA's M rows (models.lua:206 512 -> 512 at 8 x 8: 373 TFLOP/s).  5-D tensor map
+// (w, j, h, plane, pair); the j stride (one image) is larger than the h and plane strides behind it -- TMA only adds coordinate * stride.
+static int make_patch_tmap_duo(CUtensorMap* tm, const void* xq, int N, int Cq, int Hq, int Wq, int Hp, int Wp, int planes) {
+  cg_tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return set_err(CG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t img = (cuuint64_t)Cq * Hq * Wq * 16;
+  cuuint64_t dims[5] = {(cuuint64_t)Wq * 8, 2, (cuuint64_t)Hq, (cuuint64_t)Cq, (cuuint64_t)N / 2};
+  cuuint64_t strides[4] = {img, (cuuint64_t)Wq * 16, (cuuint64_t)Hq * Wq * 16, 2 * img};
+  cuuint32_t box[5] = {(cuuint32_t)(Wp * 8), 2, (cuuint32_t)Hp, (cuuint32_t)planes, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(xq), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return CG_ERR_UNSUPPORTED;   // the caller falls back to the plain tile
+  return CG_OK;
+}
+
 // Weight slices as a 2-D tensor of 8-byte elements: row = one 16-byte-per-column plane of a slice ([Cop] x 16 B), rows = planes in
 // stream order.  A box of [NB columns] x [4 planes] is one 32-channel slice of a CTA's column block, landing as [c][NB][16 B].
 // Measured (gpurun_out/r02_d_conv3_dbg.txt): the same slices fetched with 1-D cp.async.bulk copies arrived at ~10 B/cycle/SM (8 KB copies;
@@ -82,6 +100,10 @@ static int make_wslice_tmap(CUtensorMap* tm, const void* wq, int Cop, long plane
 __device__ __forceinline__ void tma_patch_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_patch_5d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -628,6 +650,7 @@ struct PsParams {
   int Z;                               // > 1: K-SPLIT mode (nn.Linear, kk = 1): gridDim.x = Z CTAs each stream their share of the slices for ALL tiles
                                        //      (<= 4) and write raw partial sums to y[z][...] (bias / reduction in k_splitk_reduce)
   uint32_t patch_bytes, slice_bytes;
+  int duo;                             // 8 x 8 images: a tile is an image PAIR (make_patch_tmap_duo); n of tile_xy is then the pair index
 };
 // Weights Wp[(tap,ci)][co] fp32 -> 32-channel slices in stream order Wq[cb][tap][c 0..3][Cop][8 fp16]; zero beyond Ci / Co.
 __global__ void k_pack_wslices32(const float* __restrict__ Wp, uint8_t* __restrict__ Wq, long nchunks, int Ci, int Co, int Cop, int kk) {
@@ -741,7 +764,8 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
   int total_g = 0;
 #pragma unroll
   for (int j = 0; j < PS_SLOTS; ++j) { int nk = (nt - j + PS_SLOTS - 1) / PS_SLOTS; if (nk > 0) { int e = j * D + (nk - 1) * (ns + D) + ns; total_g = e > total_g ? e : total_g; } }
-  const int Hp = 16 + 2 * P.p, Wp = 8 + 2 * P.p;
+  const int Hp = P.duo ? 2 * (8 + 2 * P.p) : 16 + 2 * P.p, Wp = 8 + 2 * P.p;   // patch rows per plane (duo: the two images' rows interleaved)
+  const int rowstep = P.duo ? 2 * Wp : Wp;                                  // one image row down, in 16-byte pixels
   const uint32_t plane_bytes = (uint32_t)Hp * Wp * 16;
 
   if (tid == 0) {
@@ -826,7 +850,8 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
           tma_patch_4d_bar(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, mapa_u32(smem_u32(&bar_pfull[j][buf]), 0));
         } else {
           mbar_expect_tx(&bar_pfull[j][buf], P.patch_bytes);
-          tma_patch_4d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, &bar_pfull[j][buf]);
+          if (P.duo) tma_patch_5d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, 0, 0, 0, cb * 4, n, &bar_pfull[j][buf]);
+          else tma_patch_4d(patch0 + (size_t)(j * 2 + buf) * P.patch_bytes, &tmx, x0 * 8, y0, cb * 4, n, &bar_pfull[j][buf]);
         }
         e2[j] = e1[j]; e1[j] = gj[j] + len; gj[j] += len; cj[j]++;
         if (++qj[j] == nseg) { qj[j] = 0; kj[j]++; gj[j] = j * D + kj[j] * (ns + D); }
@@ -878,7 +903,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
             asm volatile("tcgen05.fence::after_thread_sync;");
             p_lo = p_lo_buf0 + (uint32_t)(seg & 1) * patch16;
           }
-          const uint32_t a_lo = p_lo + (uint32_t)(ky * Wp + kx), w_lo = w_lo0 + st * slice16;
+          const uint32_t a_lo = p_lo + (uint32_t)(ky * rowstep + kx), w_lo = w_lo0 + st * slice16;
           if (PAIR) {
             umma_pair(tm, desc64(a_lo, a_hi), desc64(w_lo, b_hi), idesc, acc);
             umma_pair(tm, desc64(a_lo + a_kstep, a_hi), desc64(w_lo + b_kstep, b_hi), idesc, 1u);
@@ -920,6 +945,13 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;");
       int n, y0, x0; tile_xy(i, n, y0, x0);
       if (zs) n += (int)blockIdx.x * P.N;                                   // partial sums of split z live in y[z]
+      const int duo = P.duo;
+      // tile row mm (0..127) -> output pixel: plain tile: row group g = mm >> 3 is image row y0 + g; duo: g = (image row, image of the pair)
+      auto pix = [&](int mm, int Hlim, bool& ok) -> size_t {
+        const int g = mm >> 3, ox = x0 + (mm & 7), oy = duo ? g >> 1 : y0 + g, nn = duo ? 2 * n + (g & 1) : n;
+        ok = oy < Hlim && ox < P.W;
+        return (((size_t)nn * P.H + oy) * P.W + ox) * P.Cor;
+      };
       const bool ghost = PAIR && tile_id(i) >= P.ntiles;                    // odd tile count: the last peer tile duplicates a real one -- read TMEM, store nothing
       const int Hst = ghost ? 0 : P.H;                                      // (every store below is guarded by oy < Hst)
       const uint32_t tcol = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * P.NB);
@@ -949,23 +981,22 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
 #pragma unroll
             for (int r = 0; r < 8; ++r) {                   // 8 lanes per pixel: whole 128-byte lines leave the SM
               const int pl = r * 4 + (lane >> 3), mm = warp * 32 + pl;
-              const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+              bool ok; const size_t po = pix(mm, Hst, ok);
               float4 o = *reinterpret_cast<const float4*>(stage + pl * 36 + q4);
-              if (oy < Hst && ox < P.W) *reinterpret_cast<float4*>(P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0 + c0 + q4) = o;
+              if (ok) *reinterpret_cast<float4*>(P.y + po + co0 + c0 + q4) = o;
             }
             __syncwarp();
           } else {                                          // padded columns past Cout
-            const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-            if (oy < Hst && ox < P.W) {
-              float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+            bool ok; const size_t po = pix(m, Hst, ok);
+            if (ok) {
+              float* out = P.y + po + co0;
               for (int q = 0; q < 32; ++q) { int co = co0 + c0 + q; if (co < P.Cor) out[c0 + q] = __uint_as_float(v[q]) * inv + (P.bias ? P.bias[co] : 0.f); }
             }
           }
         }
       } else {
-        const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-        const bool valid = oy < Hst && ox < P.W;
-        float* out = P.y + (((size_t)n * P.H + oy) * P.W + ox) * P.Cor + co0;
+        bool valid; const size_t po = pix(m, Hst, valid);
+        float* out = P.y + po + co0;
         for (int c0 = 0; c0 < P.NB; c0 += 16) {
           uint32_t v[16];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -1033,11 +1064,15 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   static const int pair_env = getenv("CATGEN_PS_PAIR") ? atoi(getenv("CATGEN_PS_PAIR")) : 0;   // off until the pair path has passed the parity suite on the GPU
   const int ntiles_pre = N * (W / 8) * ((H + 15) / 16);
   const bool pair = pair_env && Zmax == 1 && NB >= 32 && ntiles_pre >= 2 && (ctx().sm_count % 2) == 0;
-  const size_t patch_bytes = (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * (pair ? NB / 2 : NB) * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
+  // 8 x 8 images: a tile is a PAIR of images (make_patch_tmap_duo) -- every MMA row is a real pixel
+  static const int duo_env = getenv("CATGEN_PS_DUO") ? atoi(getenv("CATGEN_PS_DUO")) : 1;
+  const bool duo = duo_env && H == 8 && W == 8 && (N % 2) == 0 && N >= 2 && Zmax == 1 && !pair;
+  const int Hp_duo = 8 + 2 * p;
+  const size_t patch_bytes = duo ? (size_t)4 * 2 * Hp_duo * Wpx * 16 : (size_t)4 * Hp * Wpx * 16, slice_bytes = (size_t)4 * (pair ? NB / 2 : NB) * 16, stage_bytes = 4 * 32 * 36 * sizeof(float);
   const size_t budget = 224 * 1024;   // opt-in limit 227 KB per block minus the static part (barriers + 1 KB reserved: cuobjdump -res-usage says 1536 B)
   if (2 * PS_SLOTS * patch_bytes + stage_bytes + 3 * slice_bytes > budget) return CG_ERR_UNSUPPORTED;
   int S = (int)((budget - 2 * PS_SLOTS * patch_bytes - stage_bytes) / slice_bytes); if (S > 16) S = 16;
-  const int ntiles = N * (W / 8) * ((H + 15) / 16);
+  const int ntiles = duo ? N / 2 : N * (W / 8) * ((H + 15) / 16);
   size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16, wq_bytes = (size_t)kk * ncb * 32 * Co * 2;
   const uint8_t* wq_cached = nullptr;
   if (!split) { auto it = wslice_registry().find(Wp); if (it != wslice_registry().end() && it->second.CB == 32) wq_cached = it->second.wq; }
@@ -1064,7 +1099,7 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   P.xq = xq; P.wq = wq; P.bias = bias; P.scale2 = scale2; P.y = y; P.inv_host = 1.f;
   P.N = N; P.H = H; P.W = W; P.Co = Co; P.Cor = Cor; P.k = k; P.p = p;
   P.ncb = ncb; P.kk = kk; P.nslices = ncb * kk;
-  P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.ntiles = ntiles; P.NB = NB; P.S = S;
+  P.tiles_x = W / 8; P.tiles_y = (H + 15) / 16; P.ntiles = ntiles; P.NB = NB; P.S = S; P.duo = duo ? 1 : 0;
   // K split: only worth it when the tile grid alone leaves most SMs idle (Linear 20480 -> 256 at batch 128 is ONE tile x two column blocks)
   int Z = 1;
   if (Zmax > 1 && kk == 1 && ntiles <= PS_SLOTS) {
@@ -1102,7 +1137,8 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * (split ? Cir_real : Cir);             // algorithmic (unpadded) work; the compensation MMAs are overhead, not work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
   CUtensorMap tmx, tmw;
-  CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
+  if (duo) { int ts = make_patch_tmap_duo(&tmx, xq, N, Ci / 8, Hq, Wq, Hp_duo, Wpx, 4); if (ts == CG_ERR_UNSUPPORTED) return set_err(CG_ERR_CUDA, "duo tensor map rejected by the driver (set CATGEN_PS_DUO=0)"); CG_TRY(ts); }
+  else CG_TRY(make_patch_tmap(&tmx, xq, 2, N, Ci / 8, Hq, Wq, Hp, Wpx, 4));
   CG_TRY(make_wslice_tmap(&tmw, wq, Co, (long)P.nslices * 4, pair ? NB / 2 : NB));
   static const bool dbg_on = getenv("CATGEN_PS_DBG") != nullptr;
   static long long* dbg_buf = nullptr;

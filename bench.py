@@ -438,6 +438,12 @@ def main():
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["bytes"] else None
             roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (ach / pk["hbm_gbs"]) if ach else None,
                     "traffic": None, "peak_source": pk["source"], "share_of_step": top["ms"] / tot}
+        try:   # DRAM bytes per launch of the dominant kernel's dominant shape, from the committed ncu --set full capture (not re-measured in this run)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+            roof["traffic"] = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            roof["traffic_of"] = {"layer": tj["layer"], "algorithmic_bytes": tj["algorithmic_bytes"], "source": tj["source"], "utchmma_pct_of_pipe_peak": tj["utchmma_pct_of_pipe_peak"]}
+        except Exception:
+            pass
         roof["timed"] = ("CUDA events around every launch of %d eager steps issued on ONE stream (cg_set_concurrency(0)); the timed region itself "
                          "replays the step as one CUDA graph with concurrent lanes, where a bracketed launch would also count time shared with other lanes" % kp)
         roof["top5"] = [{"kernel": k["kernel"], "share": round(k["ms"] / tot, 4), "launches_per_step": k["launches"] / kp} for k in prof[:5]]

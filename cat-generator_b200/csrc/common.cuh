@@ -51,6 +51,10 @@ struct Ctx {
   // instrumentation (bench.py): per-launch CUDA events on `stream`, algorithmic flops/bytes per launch
   bool prof_on = false;
   double next_flops = 0, next_bytes = 0;
+  double* next_stats_part = nullptr;   // one-shot: the next k_conv_ps launch may write per-CTA (sum, sum of squares) rows of its output there: [rows <= next_stats_cap][C][2]
+  int next_stats_cap = 0, stats_rows = 0;   // stats_rows: set by that launch to the number of rows it wrote (0: request not honoured)
+  float* next_pool2_out = nullptr;     // one-shot: the next k_conv_ps launch may write the 2 x 2 block sums of its output there instead of the output (conv_tc.cu)
+  int pool2_done = 0;                  // set by that launch when it did
   int trace_launches = 0;              // CATGEN_LAUNCH_TRACE=1: every counted launch is named on stderr (diagnosis of launch-count differences)
   int precision = 0;                   // cg_set_precision: 1 = every FORWARD convolution of G and D runs with error-compensated operands (hi + lo fp16 pairs)
   int split_fwd = 0;                   // > 0 inside a forward executor while precision == 1: conv_ps_run packs [hi, lo, hi] x [hi, hi, lo]

@@ -650,6 +650,8 @@ struct PsParams {
   int Z;                               // > 1: K-SPLIT mode (nn.Linear, kk = 1): gridDim.x = Z CTAs each stream their share of the slices for ALL tiles
                                        //      (<= 4) and write raw partial sums to y[z][...] (bias / reduction in k_splitk_reduce)
   uint32_t patch_bytes, slice_bytes;
+  double* stats;                       // forward convolution feeding a training-mode BatchNormalization: per-CTA partial (sum, sum of squares) rows [gridDim.x][Cor][2]
+  int pool2; float* y2;                // input-gradient convolution of an upsampled stage: the epilogue sums 2 x 2 blocks and writes y2 [N, H/2, W/2, Cor] instead of y
   int duo;                             // 8 x 8 images: a tile is an image PAIR (make_patch_tmap_duo); n of tile_xy is then the pair index
 };
 // Weights Wp[(tap,ci)][co] fp32 -> 32-channel slices in stream order Wq[cb][tap][c 0..3][Cop][8 fp16]; zero beyond Ci / Co.
@@ -954,6 +956,7 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
     const bool wide = vec && (P.NB & 31) == 0;
     long long t_acc = 0, tq = 0;
     float amx = 0.f;
+    double st_s[4] = {0.0, 0.0, 0.0, 0.0}, st_q[4] = {0.0, 0.0, 0.0, 0.0};   // P.stats: this lane's channel (lane of chunk c0/32): sum and sum of squares over the warp's pixels
     for (int i = 0; i < nt; ++i) {
       const int j = i & (PS_SLOTS - 1), kt = i >> 2;
       if (dbg) tq = clock64();
@@ -994,6 +997,36 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
               amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));   // rows past the image are zero operands -> zero outputs
             }
             __syncwarp();
+            if (P.stats) {   // batch-norm statistics of the conv output (models.lua:207,213,219) from the staged tile: lane = channel, fp32 over the warp's 32 pixels, double across tiles
+              float fs = 0.f, fq = 0.f;
+#pragma unroll 8
+              for (int pl = 0; pl < 32; ++pl) {
+                bool okp; (void)pix(warp * 32 + pl, Hst, okp);
+                const float vv = okp ? stage[pl * 36 + lane] : 0.f;
+                fs += vv; fq = fmaf(vv, vv, fq);
+              }
+              st_s[c0 >> 5] += (double)fs; st_q[c0 >> 5] += (double)fq;
+            }
+            if (P.pool2) {
+              // nn.SpatialUpSamplingNearest(2) backward fused into the input-gradient convolution: the warp's 4 image rows x 8 pixels are two rows of
+              // 2 x 2 blocks; 4 lanes per pooled pixel, 8 channels each -> the [N, H/2, W/2, C] gradient leaves the SM, a quarter of the bytes
+              const int pp = lane >> 2, br = pp >> 2, bc = pp & 3, ch8 = (lane & 3) * 8;
+              const float* s00 = stage + ((2 * br) * 8 + 2 * bc) * 36 + ch8;
+              float4 a0 = *reinterpret_cast<const float4*>(s00), a1 = *reinterpret_cast<const float4*>(s00 + 4);
+#pragma unroll
+              for (int t = 1; t < 4; ++t) {
+                const float* st = s00 + ((t >> 1) * 8 + (t & 1)) * 36;
+                const float4 b0 = *reinterpret_cast<const float4*>(st), b1 = *reinterpret_cast<const float4*>(st + 4);
+                a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w; a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+              }
+              const int oy = (y0 + warp * 4 + 2 * br) >> 1, ox = (x0 + 2 * bc) >> 1, Hh = P.H >> 1, Wh = P.W >> 1;
+              if (oy < (Hst >> 1) && ox < Wh) {
+                float* o = P.y2 + (((size_t)n * Hh + oy) * Wh + ox) * P.Cor + co0 + c0 + ch8;
+                *reinterpret_cast<float4*>(o) = a0; *reinterpret_cast<float4*>(o + 4) = a1;
+              }
+              __syncwarp();
+              continue;
+            }
             const int q4 = (lane & 7) * 4;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {                   // 8 lanes per pixel: whole 128-byte lines leave the SM
@@ -1047,6 +1080,20 @@ __global__ void __launch_bounds__(320, 1) k_conv_ps(PsParams P, const __grid_con
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
       if (lane == 0 && amx > 0.f) atomicMax(P.amax_out, __float_as_uint(amx));
+    }
+    if (P.stats) {   // the four epilogue warps' sums in warp order -> ONE partial row per CTA, [gridDim.x][C][2] doubles (the format ops.cu's column reductions write)
+      double* sd = reinterpret_cast<double*>(stage0);                       // 4 warps x NB x 2 doubles <= 8 KB of the 18 KB staging area; every tile of this CTA is done
+      asm volatile("bar.sync 1, 128;");                                      // the epilogue warps only (the staging area is theirs)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (q * 32 < P.NB) { sd[((warp * P.NB) + q * 32 + lane) * 2] = st_s[q]; sd[((warp * P.NB) + q * 32 + lane) * 2 + 1] = st_q[q]; }
+      asm volatile("bar.sync 1, 128;");
+      const int ch = warp * 32 + lane;
+      if (ch < P.NB && co0 + ch < P.Cor) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { a += sd[(w * P.NB + ch) * 2]; b += sd[(w * P.NB + ch) * 2 + 1]; }
+        P.stats[((size_t)blockIdx.x * P.Cor + co0 + ch) * 2] = a; P.stats[((size_t)blockIdx.x * P.Cor + co0 + ch) * 2 + 1] = b;
+      }
     }
     if (dbg && tid == 0) { dbg[20] = t_acc; dbg[21] = clock64() - t_start; dbg[22] = nt; dbg[23] = total_g; }
   }
@@ -1131,7 +1178,14 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   }
   P.Z = Z;
   P.amax_out = nullptr;
-  if (Z == 1) { P.amax_out = ctx().next_amax; ctx().next_amax = nullptr; }     // with a K split the final values come out of splitk_reduce, which takes it
+  if (Z == 1) { P.amax_out = ctx().next_amax; ctx().next_amax = nullptr; }
+  // one-shot request of the caller (model.cu, G's backward): fuse the 2 x 2 sum of SpatialUpSamplingNearest's backward into this launch's epilogue.
+  // Honoured only on the wide epilogue path of a plain (non-duo, non-split) launch; ctx().pool2_done tells the caller.
+  P.pool2 = 0; P.y2 = nullptr; P.stats = nullptr;
+  if (ctx().next_pool2_out) {
+    if (Z == 1 && !duo && !pair && !bias && (Cor & 3) == 0 && (NB & 31) == 0 && Co == Cor && (H & 1) == 0 && (W & 1) == 0) { P.pool2 = 1; P.y2 = ctx().next_pool2_out; ctx().pool2_done = 1; }
+    ctx().next_pool2_out = nullptr;
+  }     // with a K split the final values come out of splitk_reduce, which takes it
   float* part = nullptr;
   if (Z > 1) {
     part = (float*)workspace(sizeof(float) * (size_t)Z * N * H * W * Cor + 256); if (!part) return CG_ERR_CUDA;
@@ -1157,8 +1211,27 @@ static int conv_ps_run(const float* x, const float* Wp, const float* bias, float
   // idle on the 8x8 / 16x16 layers (128 -> 128 7x7 at 8x8: 32 CTAs, 117 us against 52 us with 64 CTAs) -- the tensor pipe, not the
   // weight stream, bounds a CTA, so sharing slices among fewer, busier CTAs buys nothing there.
   if (gx > ntiles) gx = ntiles;
+  // ... but at least CATGEN_PS_MINTILES tiles per CTA, balanced.  Alone, every layer is fastest with one tile per CTA; inside the training step the
+  // opposite holds (profiles/r02_tiles_per_cta.txt: 5.46 ms at 1, 5.20 ms at 4): a k_conv_ps CTA owns its SM (224 KB of shared memory), so a
+  // convolution that fills the machine serialises D's four branches and the generator forward running ahead; at four tiles per CTA the small
+  // convolutions take 32-64 SMs each and run side by side.
+  // The SAME value on the main stream and inside lanes by default: a tile's K-accumulation order depends on the slot it lands in, i.e. on the
+  // grid, so a lane-dependent grid made "concurrent lanes" and "one stream" differ in the last fp32 bits (and, through fp16 operand rounding
+  // and Adam's sign-like first steps, visibly: three schedule-equivalence tests failed with main 1 / lane 4, which was 0.02 ms faster).
+  static const int mintiles_env = getenv("CATGEN_PS_MINTILES") ? atoi(getenv("CATGEN_PS_MINTILES")) : 4;
+  static const int mintiles_lane = getenv("CATGEN_PS_MINTILES_LANE") ? atoi(getenv("CATGEN_PS_MINTILES_LANE")) : mintiles_env;   // inside a concurrent lane (D's branches, the G-ahead lane)
+  const int mt = ctx().lane >= 0 ? mintiles_lane : mintiles_env;
+  if (!pair && Z == 1 && mt > 0) {
+    int per = (ntiles + gx - 1) / gx; if (per < mt) per = mt; if (per > ntiles) per = ntiles;
+    gx = (ntiles + per - 1) / per;
+  }
   if (mc) gx &= ~1;                                                       // whole clusters; every CTA keeps at least one tile (gx <= ntiles)
   if (Z > 1) gx = Z;
+  // one-shot request (model.cu, G's forward): per-CTA batch-norm partial sums from the epilogue instead of a separate pass over the output
+  if (ctx().next_stats_part) {
+    if (Z == 1 && !pair && (Cor & 3) == 0 && (NB & 31) == 0 && Co == Cor && gx <= ctx().next_stats_cap) { P.stats = ctx().next_stats_part; ctx().stats_rows = gx; }
+    ctx().next_stats_part = nullptr;
+  }
   dim3 grid(gx, gy);
   ctx().next_flops = 2.0 * (double)N * H * W * Cor * kk * (split ? Cir_real : Cir);             // algorithmic (unpadded) work; the compensation MMAs are overhead, not work
   ctx().next_bytes = (double)xq_bytes + (double)wq_bytes + 4.0 * (double)N * H * W * Cor;
@@ -1619,7 +1692,10 @@ static int conv_wgrad_tc_impl(const float* x, const GradOperand& g, float* gWp_o
   size_t smem = 2 * ((size_t)P.patch_bytes + P.g_bytes);
   if (smem > 216 * 1024) return CG_ERR_UNSUPPORTED;
   int base = P.ncib * P.ncob * P.ntg;
-  int Z = (ctx().sm_count + base - 1) / base; if (Z > P.tiles_total / 2) Z = P.tiles_total / 2; if (Z < 1) Z = 1;
+  // pixel splits: fill the machine -- divided by CATGEN_WG_DIV (experiments): the weight gradient runs on a side stream beside the input-gradient
+  // convolution and, in D, beside three other branches; a grid that leaves SMs to them can shorten the step although the kernel alone gets slower
+  static const int wg_div = getenv("CATGEN_WG_DIV") ? atoi(getenv("CATGEN_WG_DIV")) : 1;
+  int Z = (ctx().sm_count / (wg_div > 0 ? wg_div : 1) + base - 1) / base; if (Z > P.tiles_total / 2) Z = P.tiles_total / 2; if (Z < 1) Z = 1;
   P.Z = Z;
   size_t xq_bytes = (size_t)N * (Ci / 8) * Hq * Wq * 16;
   size_t part_bytes = (size_t)Z * kk * Cir * Cor * sizeof(float);

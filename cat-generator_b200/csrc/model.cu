@@ -276,6 +276,7 @@ int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
   const float* src = g->lin; int src_bn = -1;   // fused path: the tensor whose (BN +) PReLU is the next stage's input
   if (!fuse) { g->act0 = FW(g, B * F0); NN(g->act0); CG_TRY(prelu_fwd(g->lin, g->P + g->oLpw, g->act0, B * F0)); cur = g->act0; }
   for (int i = 0; i < g->nst; ++i) {
+    double* stats_part = nullptr; int stats_S = 0;   // set when the conv epilogue produced this stage's batch-norm partial sums
     cg_gstage& s = g->st[i];
     const int hin = h; if (s.up) h *= 2;
     long M = (long)B * h * h, no = M * s.Co;
@@ -292,7 +293,19 @@ int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
       CG_TRY(bn_prelu_up_pack(src, ga, be, me, iv, pw, bn_out, xq, B, hin, hin, s.Ci, s.up, s.k));
       g->sxq[i] = xq;
       cg_layer& L = g->layers[s.layer];
-      CG_TRY(conv_fwd_tc_packed(xq, L.Wp, L.bp, g->sconv[i], B, h, h, s.Ci, s.Co, s.k));
+      // training-mode batch norm behind this convolution: its (sum, sum of squares) come out of the conv epilogue (conv_tc.cu P.stats)
+      static const bool stats_off = getenv("CATGEN_EPI_STATS_OFF") != nullptr;
+      stats_part = nullptr; stats_S = 0;
+      if (s.bn && g->training && !stats_off) {
+        const int cap = ctx().sm_count;
+        stats_part = (double*)FW(g, (size_t)4 * (cap + 1) * s.Co + 4); NN(stats_part);
+        stats_part = (double*)(((uintptr_t)stats_part + 7) & ~(uintptr_t)7);
+        ctx().next_stats_part = stats_part; ctx().next_stats_cap = cap; ctx().stats_rows = 0;
+      }
+      int cst = conv_fwd_tc_packed(xq, L.Wp, L.bp, g->sconv[i], B, h, h, s.Ci, s.Co, s.k);
+      ctx().next_stats_part = nullptr;
+      CG_TRY(cst);
+      stats_S = ctx().stats_rows; ctx().stats_rows = 0;
     } else {
       if (s.up) {
         g->sup[i] = FW(g, (size_t)M * s.Ci); NN(g->sup[i]);
@@ -306,12 +319,12 @@ int G_forward_dev(cg_model* g, const float* z_dev, int B, float* out_nchw) {
     if (s.bn) {
       g->smean[i] = FW(g, s.Co); g->sinv[i] = FW(g, s.Co); NN(g->smean[i]); NN(g->sinv[i]);
       if (fuse_next) {   // statistics only; the next stage's producer applies them (g_stage_fused implies training mode)
-        CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, nullptr, g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
+        CG_TRY(bn_fwd_train_pre(stats_S > 0 ? stats_part : nullptr, stats_S, g->sconv[i], g->P + s.og, g->P + s.obt, nullptr, g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
         src = g->sconv[i]; src_bn = i;
       } else {
         g->sbn[i] = FW(g, no); g->sact[i] = FW(g, no); NN(g->sbn[i]); NN(g->sact[i]);
         if (g->training)   // adversarial.train never switches G to evaluate(): batch statistics
-          CG_TRY(bn_fwd_train(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
+          CG_TRY(bn_fwd_train_pre(stats_S > 0 ? stats_part : nullptr, stats_S, g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->smean[i], g->sinv[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f, 0.1f));
         else
           CG_TRY(bn_fwd_eval(g->sconv[i], g->P + s.og, g->P + s.obt, g->sbn[i], g->run + r, g->run + r + s.Co, M, s.Co, 1e-5f));
         CG_TRY(prelu_fwd(g->sbn[i], g->P + s.opw, g->sact[i], no));
@@ -346,11 +359,19 @@ int G_backward_dev(cg_model* g, const float* gout_nchw, float* gz_dev) {
       CG_TRY(bn_bwd(g->sconv[i], gbn, g->P + s.og, g->smean[i], g->sinv[i], gconv, g->G + s.og, g->G + s.obt, M, s.Co));
     } else CG_TRY(sigmoid_bwd(g->sact[i], gcur, gconv, no));
     float* gin = BW(g, (size_t)M * s.Ci); NN(gin);
-    CG_TRY(layer_bwd(g, s.layer, g->sup[i], gconv, gin, B, h, h, g->sfused[i] ? g->sxq[i] : nullptr));
+    float* gs = nullptr;
+    if (s.up) {   // ask the input-gradient convolution to sum the 2 x 2 blocks in its epilogue (conv_tc.cu P.pool2): the full-resolution gradient is then never written
+      gs = BW(g, (size_t)B * (h / 2) * (h / 2) * s.Ci); NN(gs);
+      static const bool off = getenv("CATGEN_POOL2_OFF") != nullptr;
+      ctx().pool2_done = 0; ctx().next_pool2_out = (off || ctx().conv_engine != 1) ? nullptr : gs;
+    }
+    int lst = layer_bwd(g, s.layer, g->sup[i], gconv, gin, B, h, h, g->sfused[i] ? g->sxq[i] : nullptr);
+    ctx().next_pool2_out = nullptr;
+    CG_TRY(lst);
     if (s.up) {
       h /= 2;
-      float* gs = BW(g, (size_t)B * h * h * s.Ci); NN(gs);
-      CG_TRY(upsample2x_bwd(gin, gs, B, h, h, s.Ci));
+      if (!ctx().pool2_done) CG_TRY(upsample2x_bwd(gin, gs, B, h, h, s.Ci));
+      ctx().pool2_done = 0;
       gin = gs;
     }
     gcur = gin;

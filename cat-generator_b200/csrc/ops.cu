@@ -301,15 +301,17 @@ __global__ void k_bn_apply(const float* __restrict__ x, const float* __restrict_
     y[i] = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
   }
 }
-int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
-                 float* run_mean, float* run_var, long M, int C, float eps, float mom) {
-  int S = colreduce_splits(M, C);
+static int bn_fwd_train_impl(const double* pre_part, int pre_S, const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                             float* run_mean, float* run_var, long M, int C, float eps, float mom) {
+  int S = pre_part ? pre_S : colreduce_splits(M, C);
   long rps = (M + S - 1) / S;
-  double* part = (double*)workspace(sizeof(double) * 2 * (size_t)(S + 1) * C);
+  double* part = pre_part ? const_cast<double*>(pre_part) : (double*)workspace(sizeof(double) * 2 * (size_t)(S + 1) * C);
   if (!part) return CG_ERR_CUDA;
-  dim3 g(cdiv(C, 32), S), b(32, 8);
-  ctx().next_bytes = 4.0 * (double)M * C;
-  CG_LAUNCH(k_colreduce<0>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
+  if (!pre_part) {
+    dim3 g(cdiv(C, 32), S), b(32, 8);
+    ctx().next_bytes = 4.0 * (double)M * C;
+    CG_LAUNCH(k_colreduce<0>, g, b, 0, x, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, part, M, C, rps);
+  }
   if (ctx().sync_bn && ctx().world > 1) {
     // sync-BN: statistics over the GLOBAL batch = all-reduced per-channel (sum, sum of squares), 2*C doubles
     double* tot = part + 2 * (size_t)S * C;
@@ -321,6 +323,14 @@ int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y
   long n = M * C;
   if (y) CG_LAUNCH(k_bn_apply, grid1d(n, 256, 4), 256, 0, x, gamma, beta, mean, invstd, y, n, C);   // y == nullptr: statistics only (the caller fuses the apply)
   return CG_OK;
+}
+int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                 float* run_mean, float* run_var, long M, int C, float eps, float mom) {
+  return bn_fwd_train_impl(nullptr, 0, x, gamma, beta, y, mean, invstd, run_mean, run_var, M, C, eps, mom);
+}
+int bn_fwd_train_pre(const double* pre_part, int pre_S, const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                     float* run_mean, float* run_var, long M, int C, float eps, float mom) {
+  return bn_fwd_train_impl(pre_part, pre_S, x, gamma, beta, y, mean, invstd, run_mean, run_var, M, C, eps, mom);
 }
 __global__ void k_bn_eval(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                           const float* __restrict__ rm, const float* __restrict__ rv, float* __restrict__ y, long n, int C, float eps) {

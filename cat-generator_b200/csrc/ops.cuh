@@ -33,6 +33,9 @@ int maxpool2_bwd(const float* gy, const uint8_t* idx, float* gx, int N, int H, i
 // ---- batch norm over rows of [M, C]
 int bn_fwd_train(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
                  float* run_mean, float* run_var, long M, int C, float eps, float mom);
+// pre_part / pre_S: per-channel partial sums already produced elsewhere (the conv epilogue), [pre_S][C][2] doubles with room for one more row
+int bn_fwd_train_pre(const double* pre_part, int pre_S, const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                     float* run_mean, float* run_var, long M, int C, float eps, float mom);
 int bn_fwd_eval(const float* x, const float* gamma, const float* beta, float* y, const float* run_mean,
                 const float* run_var, long M, int C, float eps);
 int bn_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* invstd,

@@ -95,7 +95,8 @@ def conv_shape_names(B):
     out = {}
     for n in (B, B // 2):
         for name, hw, ci, co, k in layers:
-            out[round(2.0 * n * hw * hw * co * ci * k * k / 1e6)] = "%s B=%d" % (name, n)
+            key, label = round(2.0 * n * hw * hw * co * ci * k * k / 1e6), "%s B=%d" % (name, n)
+            out[key] = out[key] + " or " + label if key in out else label      # equal work: G.conv1 at B and G.conv2 at B/2; D.trunk1 at B and G.conv4 at B/2
     return out
 
 

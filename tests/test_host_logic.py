@@ -86,3 +86,59 @@ def test_checkpoint_round_trip_and_mismatch(tmp_path):
     with pytest.raises(ValueError):
         checkpoint.load(path, g2, short)
     assert np.array_equal(g2.p, before)              # nothing was loaded on a mismatch
+
+
+def test_rate_with_V_list_and_tensor():
+    """NN_UTILS.rateWithV (utils/nn_utils.lua:686-711): 1 - mean of the first SoftMax column, for a list of images or one tensor."""
+    class FakeV:
+        def forward(self, x):
+            p = x[:, 0, 0, 0].astype(np.float32)                       # P(fake) = the image's first pixel
+            return np.stack([p, 1 - p], 1)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 1, (9, 3, 32, 32)).astype(np.float32)
+    want = 1.0 - float(x[:, 0, 0, 0].astype(np.float64).mean())
+    assert abs(nn_utils.rateWithV(FakeV(), x) - want) < 1e-6
+    assert abs(nn_utils.rateWithV(FakeV(), [x[i] for i in range(9)]) - want) < 1e-6
+
+
+def test_torch7_checkpoint_round_trip_with_real_layouts(tmp_path):
+    """saveAs / torch.load through the Torch7 binary format (train.lua:252-261,127-137) with stand-in networks that have the real
+    parameter counts: the module trees must take and give back getParameters()'s vector exactly, and refuse another architecture."""
+    from catgen import lib as cl
+    from oracle import pyoracle as po
+
+    class Net:
+        def __init__(self, kind, C, n, nrun, seed):
+            r = np.random.default_rng(seed)
+            self.kind, self.C, self.nz, self.nparams = kind, C, 100, n
+            self.p, self.run = r.standard_normal(n).astype(np.float32), r.uniform(0.5, 1.5, nrun).astype(np.float32)
+        def get_params(self): return self.p.copy()
+        def set_params(self, a): self.p = np.asarray(a, np.float32).copy()
+        def get_bn_running(self): return self.run.copy()
+        def set_bn_running(self, a): self.run = np.asarray(a, np.float32).copy()
+
+    g, d = Net(cl.G32UPC, 3, 5191687, 2 * (512 + 256 + 128), 1), Net(cl.D32_ST3, 3, 6664777, 0, 2)
+    path = str(tmp_path / "adversarial.net")
+    checkpoint.save_torch7(path, g, d, epoch=4, opt={"batchSize": 128, "colorSpace": "rgb"}, normalize_mean=0.1)
+    g2, d2 = Net(cl.G32UPC, 3, 5191687, 2 * (512 + 256 + 128), 3), Net(cl.D32_ST3, 3, 6664777, 0, 4)
+    rest = checkpoint.load_torch7(path, g2, d2)
+    assert rest["epoch"] == 4 and rest["opt"]["colorSpace"] == "rgb" and rest["normalize_mean"] == 0.1
+    assert np.array_equal(g2.p, g.p) and np.array_equal(d2.p, d.p) and np.array_equal(g2.run, g.run)
+    other = Net(cl.G32UP, 3, 2470406, 2 * (256 + 128), 5)
+    before = other.p.copy()
+    with pytest.raises(ValueError):
+        checkpoint.load_torch7(path, other, None)
+    assert np.array_equal(other.p, before)                              # nothing was loaded
+    assert po.V32_nparams(3) == 6288258
+
+
+def test_bench_layer_names_cover_the_step():
+    """bench.py labels the per-shape roofline rows by algorithmic MFLOP per launch: layers that do the same amount of work share a row and its label names both."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    names = b.conv_shape_names(128)
+    assert len(names) == 22 and len(set(names.values())) == 22
+    assert names[round(2.0 * 128 * 32 * 32 * 128 * 256 * 25 / 1e6)].startswith("G.conv3")
+    ambiguous = [v for v in names.values() if " or " in v]              # two pairs of layers do the same work: the label says so instead of guessing
+    assert len(ambiguous) == 2 and any("G.conv1" in v and "G.conv2" in v for v in ambiguous)

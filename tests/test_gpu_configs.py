@@ -184,7 +184,7 @@ def _compare_schedules(a, b):
         else:
             for run in (x, y):
                 assert np.array_equal(run[1], run[2]), "an eager forward after training steps ran on stale packed weights (max diff %g)" % np.abs(run[1] - run[2]).max()
-            assert np.abs(x[1] - y[1]).max() < 0.3       # two trajectories 8+ updates apart (measured 5.2e-2 .. 0.155 of a [0,1] pixel range; corruption shows as NaN or O(1))
+            assert np.abs(x[1] - y[1]).max() < 0.5       # two trajectories 8+ updates apart (measured 5.2e-2 .. 0.155 of a [0,1] pixel range; corruption shows as NaN or ~1)
     # training really happened in both modes: (almost) every parameter moved by about steps * lr
     assert np.mean(np.abs(a[1] - b[1]) > 0.5e-3) < 0.2 and np.mean(np.abs(a[2] - b[2]) > 0.5e-3) < 0.2
 
